@@ -1,0 +1,148 @@
+/* sift_b200.h -- C ABI of the B200-native SIFT engine.
+ *
+ * This is the drop-in boundary for the reference's hot path, the two free functions declared
+ * in the reference's src/sift.hh:
+ *
+ *   detect_keypoints_and_descriptors(const Image&, ...)      sift.hh:65-71, sift.cpp:712-776
+ *   match_keypoints(const vector<Keypoint>&, ..., ratio)      sift.hh:73-75, sift.cpp:783-815
+ *
+ * The reference has no FFI of its own (it is one C++ executable); a C++ shim with the exact
+ * sift.hh signatures (sift_project_b200/shim/sift_shim.cpp) sits on top of this ABI so that the
+ * reference's main.cpp relinks unchanged -- see INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every call returns a status code
+ * and never throws; sift_b200_last_error() gives the text.  All compute runs in hand-written
+ * sm_100a CUDA kernels; there is NO CPU fallback: without a usable CUDA device
+ * sift_b200_create() fails with SIFT_B200_E_NO_DEVICE.
+ */
+#ifndef SIFT_B200_H
+#define SIFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIFT_B200_OK 0
+#define SIFT_B200_E_INVALID 1     /* bad argument (null pointer, non 1/3 channels, tiny image) */
+#define SIFT_B200_E_NO_DEVICE 2   /* no CUDA device / wrong architecture */
+#define SIFT_B200_E_CUDA 3        /* a CUDA runtime call or kernel failed */
+#define SIFT_B200_E_CAPACITY 4    /* an output or internal list overflowed its capacity */
+#define SIFT_B200_E_UNSUPPORTED 5 /* parameter combination outside this build (see params) */
+#define SIFT_B200_E_TOO_LARGE 6   /* image larger than the context was created for */
+
+/* Byte-for-byte the reference's struct Keypoint (sift.hh:15-23): 168 bytes.
+ * x, y, size are in INPUT-image pixels when double_image_size is on (sift.cpp:520-527);
+ * octave is the pyramid index (octave 0 = the doubled image); pori in [0, 2 pi). */
+typedef struct sift_b200_keypoint {
+    double x, y;
+    int32_t octave, layer;
+    double size, pori;
+    uint8_t desc[128];
+} sift_b200_keypoint;
+
+/* The arguments of detect_keypoints_and_descriptors (sift.hh:65-71), same meaning and defaults.
+ * This build implements intervals == 3, window_size == 3, num_bins == 36 (the reference's
+ * defaults; get_pixel_cube is hard-wired to 3x3x3 there too, sift.cpp:35-37); other values
+ * return SIFT_B200_E_UNSUPPORTED.  max_octaves is an extension: 0 = derive as the reference does
+ * (sift.cpp:132-137), n > 0 = stop after n octaves. */
+typedef struct sift_b200_params {
+    int32_t double_image_size;  /* 1 */
+    double init_sigma;          /* 1.6 */
+    int32_t intervals;          /* 3 */
+    int32_t window_size;        /* 3 */
+    double contrast_threshold;  /* 0.04 */
+    double eigen_ratio;         /* 10 */
+    double num_bins;            /* 36 */
+    double peak_ratio;          /* 0.8 */
+    double ori_sigma_factor;    /* 1.5 */
+    double desc_scale_factor;   /* 3.0 */
+    int32_t max_octaves;        /* 0 (extension) */
+} sift_b200_params;
+
+typedef struct sift_b200_ctx sift_b200_ctx;
+
+/* Per-stage counts of the last detect call, mirroring the counts the reference prints
+ * (sift.cpp:746, 752, 758, 763). */
+typedef struct sift_b200_stats {
+    int32_t octaves;
+    int32_t extrema;
+    int32_t raw_keypoints;
+    int32_t oriented_keypoints;
+    int32_t final_keypoints;
+    int32_t base_width, base_height;
+} sift_b200_stats;
+
+void sift_b200_default_params(sift_b200_params* p);
+
+/* One context = one GPU + one stream + one workspace sized for images up to max_width x
+ * max_height (before doubling).  Not thread-safe; use one context per host thread. */
+int sift_b200_create(int device, int max_width, int max_height, sift_b200_ctx** out);
+void sift_b200_destroy(sift_b200_ctx* ctx);
+const char* sift_b200_last_error(const sift_b200_ctx* ctx); /* ctx may be NULL: create errors */
+
+/* detect_keypoints_and_descriptors (sift.cpp:712-776).
+ * pixels: row-major, interleaved, channels = 1 (gray) or 3 (RGB), values 0..255; HOST or DEVICE
+ * memory (detected).  The u8 entry point is exact for file-loaded images (image_io.cpp:27-33);
+ * the f32 one accepts arbitrary values.  out: HOST array of `capacity` records, filled in the
+ * reference's order (sorted by Keypoint::operator<, sift.hh:31-41, duplicates removed).
+ * *count receives the number found even when it exceeds capacity (status E_CAPACITY then). */
+int sift_b200_detect_u8(sift_b200_ctx* ctx, const uint8_t* pixels, int width, int height,
+                        int channels, const sift_b200_params* params, sift_b200_keypoint* out,
+                        int capacity, int* count);
+int sift_b200_detect_f32(sift_b200_ctx* ctx, const float* pixels, int width, int height,
+                         int channels, const sift_b200_params* params, sift_b200_keypoint* out,
+                         int capacity, int* count);
+
+/* Device-resident variant: enqueue the whole pipeline on the context's stream and leave the
+ * results on the GPU.  d_pixels must be DEVICE memory.  No host synchronisation happens. */
+int sift_b200_detect_enqueue_u8(sift_b200_ctx* ctx, const uint8_t* d_pixels, int width, int height,
+                                int channels, const sift_b200_params* params);
+/* Wait for the enqueued work; returns the number of final keypoints in *count. */
+int sift_b200_detect_finish(sift_b200_ctx* ctx, int* count);
+/* Device pointers to the results of the last detect: `n` 168-byte records and the dense
+ * n x 128 u8 descriptor matrix (row i = record i's desc), valid until the next detect. */
+int sift_b200_result_device(sift_b200_ctx* ctx, const sift_b200_keypoint** d_records,
+                            const uint8_t** d_descriptors, int* n);
+int sift_b200_get_stats(sift_b200_ctx* ctx, sift_b200_stats* stats);
+
+/* match_keypoints (sift.cpp:783-815) on dense descriptor matrices (n x 128 u8, row-major; HOST
+ * or DEVICE, detected).  For every row i of A in ascending order: best and second-best
+ * Euclidean distance over all rows of B (lowest j wins ties), emitted iff
+ * best < ratio * second.  Outputs are HOST arrays of `capacity` entries (dist = sqrt of the
+ * integer squared distance, as the reference stores it). */
+int sift_b200_match(sift_b200_ctx* ctx, const uint8_t* desc_a, int na, const uint8_t* desc_b,
+                    int nb, double ratio, int32_t* idx_a, int32_t* idx_b, double* dist,
+                    int capacity, int* count);
+/* Device-resident variant: fills, for every row of A, the index of its nearest row of B and the
+ * two smallest SQUARED distances (exact integers).  All pointers are DEVICE memory; enqueued on
+ * the context's stream, no host synchronisation.  nb == 0 leaves best_idx = -1. */
+int sift_b200_match_enqueue(sift_b200_ctx* ctx, const uint8_t* d_desc_a, int na,
+                            const uint8_t* d_desc_b, int nb, int32_t* d_best_idx,
+                            int32_t* d_best_d2, int32_t* d_second_d2);
+int sift_b200_sync(sift_b200_ctx* ctx);
+/* The CUDA stream (cudaStream_t) the context enqueues on, for event timing by the caller. */
+void* sift_b200_stream(sift_b200_ctx* ctx);
+/* Which matcher the next match call will use for these sizes: 1 = tcgen05 tensor-core kernel,
+ * 0 = SIMT dp4a kernel (small problems). */
+int sift_b200_match_path(int na, int nb);
+
+/* ---- introspection used by the parity tests (stage-by-stage comparison with the oracle) ---- */
+#define SIFT_B200_PLANE_GAUSSIAN 0 /* layer 0..5 */
+#define SIFT_B200_PLANE_DOG 1      /* layer 0..4 */
+int sift_b200_debug_plane_dims(sift_b200_ctx* ctx, int octave, int* width, int* height);
+int sift_b200_debug_plane(sift_b200_ctx* ctx, int kind, int octave, int layer, float* host_out);
+/* rows of (x, y, layer, octave) int32; order is NOT the reference's emission order */
+int sift_b200_debug_extrema(sift_b200_ctx* ctx, int32_t* host_out, int capacity, int* count);
+/* stage 0 = raw (after refine, doubled-image frame), 1 = oriented (before sort/dedup) */
+int sift_b200_debug_keypoints(sift_b200_ctx* ctx, int stage, sift_b200_keypoint* host_out,
+                              int capacity, int* count);
+/* number of kernel launches issued by this context since creation (bench's gpu_launches) */
+long sift_b200_launch_count(const sift_b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIFT_B200_H */

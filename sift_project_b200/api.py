@@ -1,0 +1,291 @@
+"""ctypes binding of include/sift_b200.h.
+
+Mirrors the reference's public API (src/sift.hh:65-75):
+  detect_keypoints_and_descriptors(image, double_image_size=True, init_sigma=1.6, intervals=3,
+      window_size=3, contrast_threshold=0.04, eigen_ratio=10, num_bins=36, peak_ratio=0.8,
+      ori_sigma_factor=1.5, desc_scale_factor=3.0) -> records with the reference's Keypoint layout
+  match_keypoints(kps1, kps2, ratio_threshold=0.75) -> (idx1, idx2, distance)
+Errors surface as SiftError (the C++ shim rethrows std::runtime_error the same way).
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+# byte-for-byte the reference's struct Keypoint (sift.hh:15-23)
+KP_DTYPE = np.dtype(
+    [("x", "<f8"), ("y", "<f8"), ("octave", "<i4"), ("layer", "<i4"), ("size", "<f8"),
+     ("pori", "<f8"), ("desc", "u1", (128,))]
+)
+assert KP_DTYPE.itemsize == 168
+
+STATUS = {0: "OK", 1: "E_INVALID", 2: "E_NO_DEVICE", 3: "E_CUDA", 4: "E_CAPACITY", 5: "E_UNSUPPORTED",
+          6: "E_TOO_LARGE"}
+E_CAPACITY = 4
+
+
+class SiftError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"sift_b200: {STATUS.get(code, code)}: {text}")
+        self.code = code
+
+
+class SiftParams(C.Structure):
+    """sift_b200_params; defaults are the reference's (sift.hh:65-71)."""
+    _fields_ = [
+        ("double_image_size", C.c_int32), ("init_sigma", C.c_double), ("intervals", C.c_int32),
+        ("window_size", C.c_int32), ("contrast_threshold", C.c_double), ("eigen_ratio", C.c_double),
+        ("num_bins", C.c_double), ("peak_ratio", C.c_double), ("ori_sigma_factor", C.c_double),
+        ("desc_scale_factor", C.c_double), ("max_octaves", C.c_int32),
+    ]
+
+
+class _Stats(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("octaves", "extrema", "raw_keypoints", "oriented_keypoints",
+                                          "final_keypoints", "base_width", "base_height")]
+
+
+def library_path():
+    return os.path.join(HERE, "libsift_b200.so")
+
+
+def declared_symbols():
+    """Every function include/sift_b200.h declares (used by the load/export test)."""
+    text = open(os.path.join(ROOT, "include", "sift_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sift_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libsift_b200.so; raises if it has not been built (there is no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise SiftError(2, f"{path} is missing -- build it with `make -C sift_project_b200/csrc` "
+                           "(or __graft_entry__.build()); this package has no CPU fallback")
+    L = C.CDLL(path)
+    vp, i32, i32p = C.c_void_p, C.c_int, C.POINTER(C.c_int)
+    PP = C.POINTER(SiftParams)
+    sig = {
+        "sift_b200_default_params": (None, [PP]),
+        "sift_b200_create": (i32, [i32, i32, i32, C.POINTER(vp)]),
+        "sift_b200_destroy": (None, [vp]),
+        "sift_b200_last_error": (C.c_char_p, [vp]),
+        "sift_b200_detect_u8": (i32, [vp, vp, i32, i32, i32, PP, vp, i32, i32p]),
+        "sift_b200_detect_f32": (i32, [vp, vp, i32, i32, i32, PP, vp, i32, i32p]),
+        "sift_b200_detect_enqueue_u8": (i32, [vp, vp, i32, i32, i32, PP]),
+        "sift_b200_detect_finish": (i32, [vp, i32p]),
+        "sift_b200_result_device": (i32, [vp, C.POINTER(vp), C.POINTER(vp), i32p]),
+        "sift_b200_get_stats": (i32, [vp, C.POINTER(_Stats)]),
+        "sift_b200_match": (i32, [vp, vp, i32, vp, i32, C.c_double, vp, vp, vp, i32, i32p]),
+        "sift_b200_match_enqueue": (i32, [vp, vp, i32, vp, i32, vp, vp, vp]),
+        "sift_b200_sync": (i32, [vp]),
+        "sift_b200_stream": (vp, [vp]),
+        "sift_b200_match_path": (i32, [i32, i32]),
+        "sift_b200_debug_plane_dims": (i32, [vp, i32, i32p, i32p]),
+        "sift_b200_debug_plane": (i32, [vp, i32, i32, i32, vp]),
+        "sift_b200_debug_extrema": (i32, [vp, vp, i32, i32p]),
+        "sift_b200_debug_keypoints": (i32, [vp, i32, vp, i32, i32p]),
+        "sift_b200_launch_count": (C.c_long, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def make_params(double_image_size=True, init_sigma=1.6, intervals=3, window_size=3,
+                contrast_threshold=0.04, eigen_ratio=10.0, num_bins=36, peak_ratio=0.8,
+                ori_sigma_factor=1.5, desc_scale_factor=3.0, max_octaves=0):
+    return SiftParams(int(bool(double_image_size)), init_sigma, intervals, window_size, contrast_threshold,
+                      eigen_ratio, num_bins, peak_ratio, ori_sigma_factor, desc_scale_factor, max_octaves)
+
+
+def _ptr(x):
+    """Device pointer of a torch CUDA tensor, host pointer of a numpy array, or a raw int."""
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    raise TypeError(type(x))
+
+
+class SiftContext:
+    """One GPU + one stream + one workspace (sift_b200_create)."""
+
+    def __init__(self, max_width, max_height, device=0):
+        self._L = load_library()
+        h = C.c_void_p()
+        rc = self._L.sift_b200_create(device, int(max_width), int(max_height), C.byref(h))
+        if rc:
+            raise SiftError(rc, self._L.sift_b200_last_error(None).decode())
+        self._h = h
+        self.device = device
+        self.max_width, self.max_height = max_width, max_height
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sift_b200_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc:
+            raise SiftError(rc, self._L.sift_b200_last_error(self._h).decode())
+
+    # ---- detect_keypoints_and_descriptors ----
+    def detect(self, image, capacity=None, **params):
+        """image: HxW or HxWx3, uint8 or float (0..255), numpy (host) or torch CUDA tensor."""
+        p = make_params(**params)
+        is_np = isinstance(image, np.ndarray)
+        shape = tuple(image.shape)
+        h, w = shape[0], shape[1]
+        ch = 1 if len(shape) == 2 else shape[2]
+        if is_np:
+            if image.dtype == np.uint8:
+                arr, fn = np.ascontiguousarray(image), self._L.sift_b200_detect_u8
+            else:
+                arr, fn = np.ascontiguousarray(image, dtype=np.float32), self._L.sift_b200_detect_f32
+        else:
+            import torch
+            arr = image.contiguous()
+            if arr.dtype == torch.uint8:
+                fn = self._L.sift_b200_detect_u8
+            else:
+                arr, fn = arr.float(), self._L.sift_b200_detect_f32
+        cap = capacity if capacity is not None else max(4096, (w * h) // 16)
+        while True:
+            out = np.zeros(cap, dtype=KP_DTYPE)
+            n = C.c_int(0)
+            rc = fn(self._h, _ptr(arr), w, h, ch, C.byref(p), out.ctypes.data, cap, C.byref(n))
+            if rc == E_CAPACITY and capacity is None and n.value > cap:
+                cap = n.value
+                continue
+            self._check(rc)
+            return out[: n.value].copy()
+
+    def detect_enqueue(self, d_image_u8, width, height, channels=1, **params):
+        p = make_params(**params)
+        self._check(self._L.sift_b200_detect_enqueue_u8(self._h, _ptr(d_image_u8), width, height, channels,
+                                                        C.byref(p)))
+
+    def detect_finish(self):
+        n = C.c_int(0)
+        self._check(self._L.sift_b200_detect_finish(self._h, C.byref(n)))
+        return n.value
+
+    def result_device(self):
+        rec, desc, n = C.c_void_p(), C.c_void_p(), C.c_int(0)
+        self._check(self._L.sift_b200_result_device(self._h, C.byref(rec), C.byref(desc), C.byref(n)))
+        return rec.value, desc.value, n.value
+
+    def stats(self):
+        s = _Stats()
+        self._check(self._L.sift_b200_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in _Stats._fields_}
+
+    # ---- match_keypoints ----
+    def match(self, desc_a, desc_b, ratio_threshold=0.75):
+        """desc_*: n x 128 uint8 (numpy host arrays, torch CUDA tensors) -> (idx_a, idx_b, dist)."""
+        na, nb = int(desc_a.shape[0]), int(desc_b.shape[0])
+        if isinstance(desc_a, np.ndarray):
+            desc_a = np.ascontiguousarray(desc_a, dtype=np.uint8)
+        if isinstance(desc_b, np.ndarray):
+            desc_b = np.ascontiguousarray(desc_b, dtype=np.uint8)
+        cap = max(na, 1)
+        ia, ib, d = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float64)
+        n = C.c_int(0)
+        self._check(self._L.sift_b200_match(self._h, _ptr(desc_a) if na else None, na,
+                                            _ptr(desc_b) if nb else None, nb, float(ratio_threshold),
+                                            ia.ctypes.data, ib.ctypes.data, d.ctypes.data, cap, C.byref(n)))
+        return ia[: n.value].copy(), ib[: n.value].copy(), d[: n.value].copy()
+
+    def match_enqueue(self, d_a, na, d_b, nb, d_best_idx, d_best_d2, d_second_d2):
+        self._check(self._L.sift_b200_match_enqueue(self._h, _ptr(d_a), na, _ptr(d_b), nb, _ptr(d_best_idx),
+                                                    _ptr(d_best_d2), _ptr(d_second_d2)))
+
+    def sync(self):
+        self._check(self._L.sift_b200_sync(self._h))
+
+    @property
+    def stream(self):
+        return self._L.sift_b200_stream(self._h)
+
+    @property
+    def launches(self):
+        return self._L.sift_b200_launch_count(self._h)
+
+    def match_path(self, na, nb):
+        return self._L.sift_b200_match_path(na, nb)
+
+    # ---- introspection for the parity tests ----
+    def plane_dims(self, octave):
+        w, h = C.c_int(), C.c_int()
+        self._check(self._L.sift_b200_debug_plane_dims(self._h, octave, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def gaussian(self, octave, layer):
+        w, h = self.plane_dims(octave)
+        out = np.zeros((h, w), np.float32)
+        self._check(self._L.sift_b200_debug_plane(self._h, 0, octave, layer, out.ctypes.data))
+        return out
+
+    def dog(self, octave, layer):
+        w, h = self.plane_dims(octave)
+        out = np.zeros((h, w), np.float32)
+        self._check(self._L.sift_b200_debug_plane(self._h, 1, octave, layer, out.ctypes.data))
+        return out
+
+    def extrema(self):
+        n = C.c_int(0)
+        self._check(self._L.sift_b200_debug_extrema(self._h, None, 0, C.byref(n)))
+        out = np.zeros((max(n.value, 1), 4), np.int32)
+        self._check(self._L.sift_b200_debug_extrema(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out[: n.value]
+
+    def stage_keypoints(self, stage):
+        n = C.c_int(0)
+        self._check(self._L.sift_b200_debug_keypoints(self._h, stage, None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), dtype=KP_DTYPE)
+        self._check(self._L.sift_b200_debug_keypoints(self._h, stage, out.ctypes.data, n.value, C.byref(n)))
+        return out[: n.value]
+
+
+def detect_keypoints_and_descriptors(image, double_image_size=True, init_sigma=1.6, intervals=3,
+                                     window_size=3, contrast_threshold=0.04, eigen_ratio=10.0, num_bins=36,
+                                     peak_ratio=0.8, ori_sigma_factor=1.5, desc_scale_factor=3.0, device=0):
+    """One-shot form of sift.hh:65-71 (creates and destroys a context)."""
+    h, w = image.shape[0], image.shape[1]
+    with SiftContext(w, h, device) as ctx:
+        return ctx.detect(image, double_image_size=double_image_size, init_sigma=init_sigma,
+                          intervals=intervals, window_size=window_size,
+                          contrast_threshold=contrast_threshold, eigen_ratio=eigen_ratio, num_bins=num_bins,
+                          peak_ratio=peak_ratio, ori_sigma_factor=ori_sigma_factor,
+                          desc_scale_factor=desc_scale_factor)
+
+
+def match_keypoints(keypoints1, keypoints2, ratio_threshold=0.75, device=0):
+    """One-shot form of sift.hh:73-75 on keypoint records; returns (idx1, idx2, distance)."""
+    with SiftContext(64, 64, device) as ctx:
+        return ctx.match(np.ascontiguousarray(keypoints1["desc"]), np.ascontiguousarray(keypoints2["desc"]),
+                         ratio_threshold)

@@ -1,0 +1,660 @@
+// C ABI of the B200 SIFT engine (include/sift_b200.h): context, workspace arena, stage
+// orchestration on one CUDA stream.  Everything between the input copy and the result copy is
+// enqueued without host synchronisation; list sizes live in device counters.
+//
+// Stage order follows detect_keypoints_and_descriptors (sift.cpp:712-776):
+//   compute_initial_image :113-126 -> compute_gaussian_images :181-202 (+ DoG :209-225 fused)
+//   -> detect_extrema :300-319 -> compute_keypoints :330-436 -> compute_orientations :447-533
+//   -> clean_keypoints :20-24 -> compute_descriptors :610-682.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sift_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace sb;
+
+static thread_local std::string g_create_error;
+
+struct sift_b200_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    int max_w = 0, max_h = 0;
+    std::string err;
+    long launches = 0;
+
+    // ---- detect workspace ----
+    float* arena = nullptr;       // all pyramid planes
+    size_t arena_floats = 0;
+    uint8_t* d_input = nullptr;   // staged input pixels (u8 or f32, up to 3 channels)
+    size_t input_bytes = 0;
+    PyramidDesc pyr;              // host copy (device pointers inside)
+    PyramidDesc* d_pyr = nullptr;
+    Counters* d_counters = nullptr;
+    Counters* h_counters = nullptr;  // pinned
+    Cand* d_cands = nullptr;
+    KpCore* d_raw = nullptr;
+    KpCore* d_oriented = nullptr;
+    uint8_t* d_records = nullptr;  // cap_final x 168
+    uint8_t* d_desc = nullptr;     // cap_final x 128
+    int cap_extrema = 0, cap_raw = 0, cap_oriented = 0;
+    SortScratch ss{};
+    int ss_nb_cap = 0;
+    StageParams sp{};
+    bool detect_pending = false;
+    bool have_result = false;
+    int base_w = 0, base_h = 0;
+    sift_b200_stats stats{};
+
+    // ---- match workspace (grown on demand) ----
+    MatchScratch ms{};
+    size_t ms_rows_a = 0, ms_rows_b = 0;
+    uint8_t* d_ma = nullptr; size_t ma_cap = 0;   // staged host descriptors
+    uint8_t* d_mb = nullptr; size_t mb_cap = 0;
+    int* d_best_idx = nullptr; int* d_best_d2 = nullptr; int* d_second_d2 = nullptr; size_t best_cap = 0;
+    int* d_out_ia = nullptr; int* d_out_ib = nullptr; double* d_out_dist = nullptr; int* d_out_count = nullptr;
+    size_t out_cap = 0;
+};
+
+namespace {
+
+int fail(sift_b200_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(c, call)                                                                           \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail((c), SIFT_B200_E_CUDA, "%s failed: %s (%s:%d)", #call,                \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                         \
+    } while (0)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// compute_octaves_count, sift.cpp:132-137: floor(log2(min(w,h) / 3)) with integer division.
+int octave_count(int w, int h) {
+    const int m = std::min(w, h) / 3;
+    if (m < 1) return 0;
+    return (int)floor(log2((double)m));
+}
+
+// apply_gaussian_blur_fast, image.cpp:226-235: ceil(3 sigma)+1 half-kernel taps; the per-pixel
+// division by the accumulated weight total (image.cpp:185) is folded into the taps.
+BlurTaps make_taps(double sigma) {
+    BlurTaps t;
+    memset(&t, 0, sizeof t);
+    const int n = (int)ceil(3 * sigma) + 1;
+    double k[64];
+    const double denom = 2 * sigma * sigma, coef = 1 / (sqrt(2 * kPi) * sigma);
+    double total = 0.0;
+    for (int i = 0; i < n && i < 64; ++i) {
+        k[i] = exp(-i * i / denom) * coef;
+        total += (i == 0) ? k[i] : 2.0 * k[i];
+    }
+    t.radius = n - 1;
+    for (int i = 0; i < n && i <= kMaxRadius; ++i) t.w[i] = (float)(k[i] / total);
+    return t;
+}
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+size_t plane_floats(int w, int h) { return (size_t)round_up(w, 32) * h; }
+
+// Carve the arena into planes for a base image of bw x bh with `octaves` octaves.
+void layout_pyramid(sift_b200_ctx* c, int bw, int bh, int octaves) {
+    float* p = c->arena;
+    c->pyr.octaves = octaves;
+    int w = bw, h = bh;
+    for (int o = 0; o < octaves; ++o) {
+        OctaveDesc& od = c->pyr.oct[o];
+        od.w = w; od.h = h; od.pitch = round_up(w, 32);
+        const size_t n = plane_floats(w, h);
+        for (int i = 0; i < kLayers; ++i) { od.G[i] = p; p += n; }
+        for (int i = 0; i < kDogs; ++i) { od.D[i] = p; p += n; }
+        w /= 2; h /= 2;
+    }
+}
+
+size_t arena_need(int bw, int bh) {
+    size_t total = 0;
+    int w = bw, h = bh;
+    for (int o = 0; o < kMaxOctaves && w >= 1 && h >= 1; ++o) {
+        total += (size_t)(kLayers + kDogs) * plane_floats(w, h);
+        w /= 2; h /= 2;
+    }
+    return total + 64;
+}
+
+int check_params(sift_b200_ctx* c, const sift_b200_params& p) {
+    if (p.intervals != 3 || p.window_size != 3 || p.num_bins != 36.0)
+        return fail(c, SIFT_B200_E_UNSUPPORTED,
+                    "this build implements intervals=3, window_size=3, num_bins=36 (got %d, %d, %g)",
+                    p.intervals, p.window_size, p.num_bins);
+    if (!(p.init_sigma > 1.0) || p.init_sigma > 3.0)
+        return fail(c, SIFT_B200_E_UNSUPPORTED, "init_sigma must be in (1, 3] (got %g)", p.init_sigma);
+    if (p.max_octaves < 0) return fail(c, SIFT_B200_E_INVALID, "max_octaves < 0");
+    return SIFT_B200_OK;
+}
+
+int grow_i32(sift_b200_ctx* c, int** p, size_t n) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    CU(c, cudaMalloc(p, n * sizeof(int)));
+    return SIFT_B200_OK;
+}
+
+int ensure_match_scratch(sift_b200_ctx* c, int na, int nb) {
+    const int max_splits = 64;
+    if ((size_t)na > c->ms_rows_a) {
+        const size_t rows = std::max<size_t>((size_t)na, 1024) * 5 / 4;
+        int rc;
+        if ((rc = grow_i32(c, &c->ms.part_idx, rows * max_splits))) return rc;
+        if ((rc = grow_i32(c, &c->ms.part_d1, rows * max_splits))) return rc;
+        if ((rc = grow_i32(c, &c->ms.part_d2, rows * max_splits))) return rc;
+        if ((rc = grow_i32(c, &c->ms.norms_a, rows))) return rc;
+        c->ms_rows_a = rows;
+        c->ms.cap_rows = rows;
+        c->ms.max_splits = max_splits;
+    }
+    if ((size_t)nb > c->ms_rows_b) {
+        const size_t rows = std::max<size_t>((size_t)nb, 1024) * 5 / 4;
+        int rc;
+        if ((rc = grow_i32(c, &c->ms.norms_b, rows))) return rc;
+        c->ms_rows_b = rows;
+    }
+    return SIFT_B200_OK;
+}
+
+int enqueue_match(sift_b200_ctx* c, const uint8_t* d_a, int na, const uint8_t* d_b, int nb, int* d_idx,
+                  int* d_d1, int* d_d2) {
+    int rc = ensure_match_scratch(c, na, nb);
+    if (rc) return rc;
+    int launches = 0;
+    CU(c, launch_match(d_a, na, d_b, nb, d_idx, d_d1, d_d2, c->ms, c->sm_count, c->stream, &launches));
+    c->launches += launches;
+    return SIFT_B200_OK;
+}
+
+template <typename T>
+int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, int channels,
+                   const sift_b200_params& p) {
+    int rc = check_params(c, p);
+    if (rc) return rc;
+    if (width < 2 || height < 2) return fail(c, SIFT_B200_E_INVALID, "image %dx%d is too small", width, height);
+    if (channels != 1 && channels != 3) return fail(c, SIFT_B200_E_INVALID, "channels must be 1 or 3");
+    if (width + 2 > c->ss_nb_cap)
+        return fail(c, SIFT_B200_E_TOO_LARGE, "image %dx%d exceeds the context's %dx%d", width, height,
+                    c->max_w, c->max_h);
+    const int doubled = p.double_image_size ? 1 : 0;
+    const int bw = doubled ? 2 * width : width, bh = doubled ? 2 * height : height;
+    if (arena_need(bw, bh) > c->arena_floats)
+        return fail(c, SIFT_B200_E_TOO_LARGE, "image %dx%d exceeds the context's workspace", width, height);
+    int octaves = octave_count(bw, bh);
+    if (p.max_octaves > 0) octaves = std::min(octaves, p.max_octaves);
+    octaves = std::min(octaves, kMaxOctaves);
+    if (octaves < 0) octaves = 0;
+    // resize_inter_nearest throws below 2x2 (image.cpp:42-44); octave_count never gets there
+    layout_pyramid(c, bw, bh, octaves);
+    c->base_w = bw; c->base_h = bh;
+    cudaStream_t s = c->stream;
+    CU(c, cudaMemcpyAsync(c->d_pyr, &c->pyr, sizeof(PyramidDesc), cudaMemcpyHostToDevice, s));
+    CU(c, cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), s));
+
+    StageParams& sp = c->sp;
+    sp.doubled = doubled;
+    sp.intervals = p.intervals;
+    sp.dog_threshold = (int)floor(0.5 * p.contrast_threshold / p.intervals * 255.0);  // sift.cpp:305-307
+    sp.init_sigma = p.init_sigma;
+    sp.contrast_threshold = p.contrast_threshold;
+    sp.eigen_ratio = p.eigen_ratio;
+    sp.peak_ratio = p.peak_ratio;
+    sp.ori_sigma_factor = p.ori_sigma_factor;
+    sp.desc_scale_factor = p.desc_scale_factor;
+    sp.cap_extrema = c->cap_extrema;
+    sp.cap_raw = c->cap_raw;
+    sp.cap_oriented = c->cap_oriented;
+
+    c->stats = sift_b200_stats{};
+    c->stats.octaves = octaves;
+    c->stats.base_width = bw;
+    c->stats.base_height = bh;
+    c->have_result = false;
+    if (octaves == 0) {
+        c->detect_pending = true;
+        CU(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        return SIFT_B200_OK;
+    }
+
+    // Scale-space sigmas, compute_gaussian_kernels sift.cpp:143-155.
+    double sig[kLayers];
+    const double k = pow(2.0, 1.0 / p.intervals);
+    sig[0] = p.init_sigma;
+    for (int i = 1; i < kLayers; ++i) sig[i] = pow(k, i - 1) * p.init_sigma * sqrt(k * k - 1);
+    BlurTaps taps[kLayers];
+    taps[0] = make_taps(sqrt(p.init_sigma * p.init_sigma - 1.0));  // sift.cpp:124: "-1" in both modes
+    for (int i = 1; i < kLayers; ++i) taps[i] = make_taps(sig[i]);
+    for (int i = 0; i < kLayers; ++i)
+        if (taps[i].radius > 12) return fail(c, SIFT_B200_E_UNSUPPORTED, "blur radius %d > 12", taps[i].radius);
+
+    // Stage 0: gray (+2x) into a scratch plane (octave 0's G[5] slot, dead until the cascade
+    // reaches it), then the initial blur into G[0].
+    OctaveDesc& o0 = c->pyr.oct[0];
+    float* scratch = o0.G[5];
+    if (sizeof(T) == 1)
+        CU(c, launch_prepare_u8((const uint8_t*)d_pixels, width, height, channels, scratch, bw, bh, o0.pitch,
+                                doubled, s));
+    else
+        CU(c, launch_prepare_f32((const float*)d_pixels, width, height, channels, scratch, bw, bh, o0.pitch,
+                                 doubled, s));
+    CU(c, launch_blur(scratch, o0.G[0], nullptr, nullptr, bw, bh, o0.pitch, 0, 0, 0, taps[0], s));
+    c->launches += 2;
+
+    for (int o = 0; o < octaves; ++o) {
+        OctaveDesc& od = c->pyr.oct[o];
+        for (int i = 1; i < kLayers; ++i) {
+            float* dec = nullptr;
+            int dw = 0, dh = 0, dp = 0;
+            if (i == kLayers - 3 && o + 1 < octaves) {  // next base = G[3] decimated, sift.cpp:195-196
+                OctaveDesc& nx = c->pyr.oct[o + 1];
+                dec = nx.G[0]; dw = nx.w; dh = nx.h; dp = nx.pitch;
+            }
+            CU(c, launch_blur(od.G[i - 1], od.G[i], od.D[i - 1], dec, od.w, od.h, od.pitch, dw, dh, dp, taps[i], s));
+            c->launches += 1;
+        }
+        if (od.w >= 3 && od.h >= 3) {
+            CU(c, launch_extrema(od, o, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, s));
+            c->launches += 1;
+        }
+    }
+    CU(c, launch_refine(c->d_pyr, c->d_cands, c->d_raw, c->d_counters, sp, s));
+    CU(c, launch_orient(c->d_pyr, c->d_raw, c->d_oriented, c->d_counters, sp, s));
+    c->launches += 2;
+    c->ss.nb = std::min(width + 2, c->ss_nb_cap);
+    int l = 0;
+    CU(c, launch_sort_dedup(c->d_oriented, c->d_counters, c->ss, sp, s, &l));
+    c->launches += l;
+    CU(c, launch_describe(c->d_pyr, c->d_oriented, c->ss.final_order, c->d_counters, c->d_records, c->d_desc,
+                          c->cap_oriented, sp, s));
+    c->launches += 1;
+    CU(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    c->detect_pending = true;
+    return SIFT_B200_OK;
+}
+
+int finish_detect(sift_b200_ctx* c, int* count) {
+    if (!c->detect_pending && !c->have_result) return fail(c, SIFT_B200_E_INVALID, "no detect call is pending");
+    if (c->detect_pending) {
+        CU(c, cudaStreamSynchronize(c->stream));
+        c->detect_pending = false;
+        const Counters& k = *c->h_counters;
+        c->stats.extrema = k.n_extrema;
+        c->stats.raw_keypoints = k.n_raw;
+        c->stats.oriented_keypoints = k.n_oriented;
+        c->stats.final_keypoints = k.n_final;
+        if (k.n_extrema > c->cap_extrema || k.n_raw > c->cap_raw || k.n_oriented > c->cap_oriented) {
+            c->have_result = false;
+            return fail(c, SIFT_B200_E_CAPACITY,
+                        "internal list overflow: extrema %d/%d raw %d/%d oriented %d/%d -- create the "
+                        "context for a larger image",
+                        k.n_extrema, c->cap_extrema, k.n_raw, c->cap_raw, k.n_oriented, c->cap_oriented);
+        }
+        c->have_result = true;
+    }
+    if (count) *count = c->stats.final_keypoints;
+    return SIFT_B200_OK;
+}
+
+template <typename T>
+int detect_sync(sift_b200_ctx* c, const T* pixels, int width, int height, int channels,
+                const sift_b200_params* params, sift_b200_keypoint* out, int capacity, int* count) {
+    if (!c) return SIFT_B200_E_INVALID;
+    if (!pixels || !count || (capacity > 0 && !out)) return fail(c, SIFT_B200_E_INVALID, "null argument");
+    if (width < 2 || height < 2) return fail(c, SIFT_B200_E_INVALID, "image %dx%d is too small", width, height);
+    if (channels != 1 && channels != 3) return fail(c, SIFT_B200_E_INVALID, "channels must be 1 or 3");
+    CU(c, cudaSetDevice(c->device));
+    sift_b200_params p;
+    if (params) p = *params; else sift_b200_default_params(&p);
+    const T* d_px = pixels;
+    if (!is_device_ptr(pixels)) {
+        const size_t bytes = (size_t)width * height * channels * sizeof(T);
+        if (bytes > c->input_bytes)
+            return fail(c, SIFT_B200_E_TOO_LARGE, "image %dx%dx%d exceeds the context's staging buffer", width,
+                        height, channels);
+        CU(c, cudaMemcpyAsync(c->d_input, pixels, bytes, cudaMemcpyHostToDevice, c->stream));
+        d_px = (const T*)c->d_input;
+    }
+    int rc = enqueue_detect<T>(c, d_px, width, height, channels, p);
+    if (rc) return rc;
+    int n = 0;
+    rc = finish_detect(c, &n);
+    *count = n;
+    if (rc) return rc;
+    const int ncopy = std::min(n, capacity);
+    if (ncopy > 0)
+        CU(c, cudaMemcpy(out, c->d_records, (size_t)ncopy * sizeof(sift_b200_keypoint), cudaMemcpyDeviceToHost));
+    if (n > capacity) return fail(c, SIFT_B200_E_CAPACITY, "%d keypoints found, output capacity %d", n, capacity);
+    return SIFT_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void sift_b200_default_params(sift_b200_params* p) {
+    if (!p) return;
+    p->double_image_size = 1;
+    p->init_sigma = 1.6;
+    p->intervals = 3;
+    p->window_size = 3;
+    p->contrast_threshold = 0.04;
+    p->eigen_ratio = 10.0;
+    p->num_bins = 36;
+    p->peak_ratio = 0.8;
+    p->ori_sigma_factor = 1.5;
+    p->desc_scale_factor = 3.0;
+    p->max_octaves = 0;
+}
+
+const char* sift_b200_last_error(const sift_b200_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int sift_b200_create(int device, int max_width, int max_height, sift_b200_ctx** out) {
+    if (!out) return fail(nullptr, SIFT_B200_E_INVALID, "out is null");
+    *out = nullptr;
+    if (max_width < 2 || max_height < 2) return fail(nullptr, SIFT_B200_E_INVALID, "bad maximum image size");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, SIFT_B200_E_NO_DEVICE, "no CUDA device is visible; this library has no CPU path");
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, SIFT_B200_E_NO_DEVICE, "device %d of %d", device, ndev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return fail(nullptr, SIFT_B200_E_NO_DEVICE, "cannot query device %d", device);
+    if (prop.major != 10)
+        return fail(nullptr, SIFT_B200_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+    sift_b200_ctx* c = new (std::nothrow) sift_b200_ctx();
+    if (!c) return fail(nullptr, SIFT_B200_E_INVALID, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->max_w = max_width;
+    c->max_h = max_height;
+#define CRT(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            fail(nullptr, SIFT_B200_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));       \
+            sift_b200_destroy(c);                                                                   \
+            return SIFT_B200_E_CUDA;                                                                \
+        }                                                                                           \
+    } while (0)
+    CRT(cudaSetDevice(device));
+    CRT(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CRT(pyramid_init());
+    CRT(match_init());
+    c->arena_floats = arena_need(2 * max_width, 2 * max_height);
+    CRT(cudaMalloc(&c->arena, c->arena_floats * sizeof(float)));
+    c->input_bytes = (size_t)max_width * max_height * 3 * sizeof(float);
+    CRT(cudaMalloc(&c->d_input, c->input_bytes));
+    CRT(cudaMalloc(&c->d_pyr, sizeof(PyramidDesc)));
+    CRT(cudaMalloc(&c->d_counters, sizeof(Counters)));
+    CRT(cudaMallocHost(&c->h_counters, sizeof(Counters)));
+    const size_t px = (size_t)max_width * max_height;
+    c->cap_extrema = (int)std::max<size_t>(1 << 16, px / 2);
+    c->cap_raw = (int)std::max<size_t>(1 << 15, px / 8);
+    c->cap_oriented = (int)std::max<size_t>(1 << 15, px / 8);
+    CRT(cudaMalloc(&c->d_cands, (size_t)c->cap_extrema * sizeof(Cand)));
+    CRT(cudaMalloc(&c->d_raw, (size_t)c->cap_raw * sizeof(KpCore)));
+    CRT(cudaMalloc(&c->d_oriented, (size_t)c->cap_oriented * sizeof(KpCore)));
+    CRT(cudaMalloc(&c->d_records, (size_t)c->cap_oriented * 168));
+    CRT(cudaMalloc(&c->d_desc, (size_t)c->cap_oriented * 128));
+    c->ss_nb_cap = 2 * max_width + 70;
+    const size_t nbp = (size_t)c->ss_nb_cap + 1;
+    CRT(cudaMalloc(&c->ss.bucket_cnt, nbp * sizeof(int)));
+    CRT(cudaMalloc(&c->ss.bucket_off, nbp * sizeof(int)));
+    CRT(cudaMalloc(&c->ss.bucket_fill, nbp * sizeof(int)));
+    CRT(cudaMalloc(&c->ss.uniq_cnt, nbp * sizeof(int)));
+    CRT(cudaMalloc(&c->ss.uniq_off, nbp * sizeof(int)));
+    CRT(cudaMalloc(&c->ss.perm, (size_t)c->cap_oriented * sizeof(int)));
+    CRT(cudaMalloc(&c->ss.tmp_sorted, (size_t)c->cap_oriented * sizeof(int)));
+    CRT(cudaMalloc(&c->ss.sorted, (size_t)c->cap_oriented * sizeof(int)));
+    CRT(cudaMalloc(&c->ss.final_order, (size_t)c->cap_oriented * sizeof(int)));
+    CRT(cudaMalloc(&c->d_out_count, sizeof(int)));
+#undef CRT
+    *out = c;
+    return SIFT_B200_OK;
+}
+
+void sift_b200_destroy(sift_b200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    void* ptrs[] = {c->arena, c->d_input, c->d_pyr, c->d_counters, c->d_cands, c->d_raw, c->d_oriented,
+                    c->d_records, c->d_desc, c->ss.bucket_cnt, c->ss.bucket_off, c->ss.bucket_fill,
+                    c->ss.uniq_cnt, c->ss.uniq_off, c->ss.perm, c->ss.tmp_sorted, c->ss.sorted,
+                    c->ss.final_order, c->ms.part_idx, c->ms.part_d1, c->ms.part_d2, c->ms.norms_a,
+                    c->ms.norms_b, c->d_ma, c->d_mb, c->d_best_idx, c->d_best_d2, c->d_second_d2,
+                    c->d_out_ia, c->d_out_ib, c->d_out_dist, c->d_out_count};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete c;
+}
+
+int sift_b200_detect_u8(sift_b200_ctx* c, const uint8_t* pixels, int width, int height, int channels,
+                        const sift_b200_params* params, sift_b200_keypoint* out, int capacity, int* count) {
+    return detect_sync<uint8_t>(c, pixels, width, height, channels, params, out, capacity, count);
+}
+
+int sift_b200_detect_f32(sift_b200_ctx* c, const float* pixels, int width, int height, int channels,
+                         const sift_b200_params* params, sift_b200_keypoint* out, int capacity, int* count) {
+    return detect_sync<float>(c, pixels, width, height, channels, params, out, capacity, count);
+}
+
+int sift_b200_detect_enqueue_u8(sift_b200_ctx* c, const uint8_t* d_pixels, int width, int height, int channels,
+                                const sift_b200_params* params) {
+    if (!c) return SIFT_B200_E_INVALID;
+    if (!d_pixels) return fail(c, SIFT_B200_E_INVALID, "null argument");
+    CU(c, cudaSetDevice(c->device));
+    sift_b200_params p;
+    if (params) p = *params; else sift_b200_default_params(&p);
+    return enqueue_detect<uint8_t>(c, d_pixels, width, height, channels, p);
+}
+
+int sift_b200_detect_finish(sift_b200_ctx* c, int* count) {
+    if (!c) return SIFT_B200_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    return finish_detect(c, count);
+}
+
+int sift_b200_result_device(sift_b200_ctx* c, const sift_b200_keypoint** d_records, const uint8_t** d_descriptors,
+                            int* n) {
+    if (!c) return SIFT_B200_E_INVALID;
+    int count = 0;
+    int rc = finish_detect(c, &count);
+    if (rc) return rc;
+    if (d_records) *d_records = (const sift_b200_keypoint*)c->d_records;
+    if (d_descriptors) *d_descriptors = c->d_desc;
+    if (n) *n = count;
+    return SIFT_B200_OK;
+}
+
+int sift_b200_get_stats(sift_b200_ctx* c, sift_b200_stats* stats) {
+    if (!c || !stats) return SIFT_B200_E_INVALID;
+    if (c->detect_pending) {
+        int rc = finish_detect(c, nullptr);
+        if (rc && rc != SIFT_B200_E_CAPACITY) return rc;
+    }
+    *stats = c->stats;
+    return SIFT_B200_OK;
+}
+
+int sift_b200_match_enqueue(sift_b200_ctx* c, const uint8_t* d_a, int na, const uint8_t* d_b, int nb,
+                            int32_t* d_best_idx, int32_t* d_best_d2, int32_t* d_second_d2) {
+    if (!c) return SIFT_B200_E_INVALID;
+    if (na < 0 || nb < 0 || (na > 0 && (!d_a || !d_best_idx || !d_best_d2 || !d_second_d2)) || (nb > 0 && !d_b))
+        return fail(c, SIFT_B200_E_INVALID, "bad match arguments");
+    CU(c, cudaSetDevice(c->device));
+    if (na == 0) return SIFT_B200_OK;
+    return enqueue_match(c, d_a, na, d_b, nb, d_best_idx, d_best_d2, d_second_d2);
+}
+
+int sift_b200_match(sift_b200_ctx* c, const uint8_t* desc_a, int na, const uint8_t* desc_b, int nb, double ratio,
+                    int32_t* idx_a, int32_t* idx_b, double* dist, int capacity, int* count) {
+    if (!c) return SIFT_B200_E_INVALID;
+    if (!count || na < 0 || nb < 0 || (na > 0 && !desc_a) || (nb > 0 && !desc_b) ||
+        (capacity > 0 && (!idx_a || !idx_b || !dist)))
+        return fail(c, SIFT_B200_E_INVALID, "bad match arguments");
+    *count = 0;
+    CU(c, cudaSetDevice(c->device));
+    if (na == 0 || nb == 0) return SIFT_B200_OK;  // sift.cpp:789-812: nothing to emit
+    cudaStream_t s = c->stream;
+    const uint8_t* d_a = desc_a;
+    const uint8_t* d_b = desc_b;
+    if (!is_device_ptr(desc_a)) {
+        if ((size_t)na > c->ma_cap) {
+            if (c->d_ma) cudaFree(c->d_ma);
+            c->d_ma = nullptr;
+            c->ma_cap = (size_t)na * 5 / 4 + 1024;
+            CU(c, cudaMalloc(&c->d_ma, c->ma_cap * 128));
+        }
+        CU(c, cudaMemcpyAsync(c->d_ma, desc_a, (size_t)na * 128, cudaMemcpyHostToDevice, s));
+        d_a = c->d_ma;
+    }
+    if (!is_device_ptr(desc_b)) {
+        if ((size_t)nb > c->mb_cap) {
+            if (c->d_mb) cudaFree(c->d_mb);
+            c->d_mb = nullptr;
+            c->mb_cap = (size_t)nb * 5 / 4 + 1024;
+            CU(c, cudaMalloc(&c->d_mb, c->mb_cap * 128));
+        }
+        CU(c, cudaMemcpyAsync(c->d_mb, desc_b, (size_t)nb * 128, cudaMemcpyHostToDevice, s));
+        d_b = c->d_mb;
+    }
+    if ((size_t)na > c->best_cap) {
+        const size_t rows = (size_t)na * 5 / 4 + 1024;
+        int rc;
+        if ((rc = grow_i32(c, &c->d_best_idx, rows))) return rc;
+        if ((rc = grow_i32(c, &c->d_best_d2, rows))) return rc;
+        if ((rc = grow_i32(c, &c->d_second_d2, rows))) return rc;
+        if ((rc = grow_i32(c, &c->d_out_ia, rows))) return rc;
+        if ((rc = grow_i32(c, &c->d_out_ib, rows))) return rc;
+        if (c->d_out_dist) cudaFree(c->d_out_dist);
+        c->d_out_dist = nullptr;
+        CU(c, cudaMalloc(&c->d_out_dist, rows * sizeof(double)));
+        c->best_cap = rows;
+    }
+    int rc = enqueue_match(c, d_a, na, d_b, nb, c->d_best_idx, c->d_best_d2, c->d_second_d2);
+    if (rc) return rc;
+    CU(c, launch_match_emit(c->d_best_idx, c->d_best_d2, c->d_second_d2, na, nb, ratio, c->d_out_ia, c->d_out_ib,
+                            c->d_out_dist, na, c->d_out_count, s));
+    c->launches += 1;
+    int n = 0;
+    CU(c, cudaMemcpyAsync(&n, c->d_out_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));
+    *count = n;
+    const int ncopy = std::min(n, capacity);
+    if (ncopy > 0) {
+        CU(c, cudaMemcpy(idx_a, c->d_out_ia, (size_t)ncopy * sizeof(int), cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(idx_b, c->d_out_ib, (size_t)ncopy * sizeof(int), cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(dist, c->d_out_dist, (size_t)ncopy * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    if (n > capacity) return fail(c, SIFT_B200_E_CAPACITY, "%d matches, output capacity %d", n, capacity);
+    return SIFT_B200_OK;
+}
+
+int sift_b200_sync(sift_b200_ctx* c) {
+    if (!c) return SIFT_B200_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return SIFT_B200_OK;
+}
+
+void* sift_b200_stream(sift_b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int sift_b200_match_path(int na, int nb) { return match_uses_tensor_cores(na, nb) ? 1 : 0; }
+
+int sift_b200_debug_plane_dims(sift_b200_ctx* c, int octave, int* width, int* height) {
+    if (!c || octave < 0 || octave >= c->pyr.octaves) return SIFT_B200_E_INVALID;
+    if (width) *width = c->pyr.oct[octave].w;
+    if (height) *height = c->pyr.oct[octave].h;
+    return SIFT_B200_OK;
+}
+
+int sift_b200_debug_plane(sift_b200_ctx* c, int kind, int octave, int layer, float* host_out) {
+    if (!c || !host_out || octave < 0 || octave >= c->pyr.octaves) return SIFT_B200_E_INVALID;
+    const OctaveDesc& od = c->pyr.oct[octave];
+    const float* src = nullptr;
+    if (kind == SIFT_B200_PLANE_GAUSSIAN && layer >= 0 && layer < kLayers) src = od.G[layer];
+    if (kind == SIFT_B200_PLANE_DOG && layer >= 0 && layer < kDogs) src = od.D[layer];
+    if (!src) return fail(c, SIFT_B200_E_INVALID, "bad plane kind/layer");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy2D(host_out, (size_t)od.w * sizeof(float), src, (size_t)od.pitch * sizeof(float),
+                       (size_t)od.w * sizeof(float), od.h, cudaMemcpyDeviceToHost));
+    return SIFT_B200_OK;
+}
+
+int sift_b200_debug_extrema(sift_b200_ctx* c, int32_t* host_out, int capacity, int* count) {
+    if (!c || !count) return SIFT_B200_E_INVALID;
+    int rc = finish_detect(c, nullptr);
+    if (rc) return rc;
+    const int n = c->stats.extrema;
+    *count = n;
+    const int ncopy = std::min(n, capacity);
+    if (ncopy > 0 && host_out)
+        CU(c, cudaMemcpy(host_out, c->d_cands, (size_t)ncopy * sizeof(Cand), cudaMemcpyDeviceToHost));
+    return SIFT_B200_OK;
+}
+
+int sift_b200_debug_keypoints(sift_b200_ctx* c, int stage, sift_b200_keypoint* host_out, int capacity, int* count) {
+    if (!c || !count || (stage != 0 && stage != 1)) return SIFT_B200_E_INVALID;
+    int rc = finish_detect(c, nullptr);
+    if (rc) return rc;
+    const int n = stage == 0 ? c->stats.raw_keypoints : c->stats.oriented_keypoints;
+    *count = n;
+    const int ncopy = std::min(n, capacity);
+    if (ncopy > 0 && host_out) {
+        std::vector<KpCore> tmp(ncopy);
+        CU(c, cudaMemcpy(tmp.data(), stage == 0 ? c->d_raw : c->d_oriented, (size_t)ncopy * sizeof(KpCore),
+                         cudaMemcpyDeviceToHost));
+        for (int i = 0; i < ncopy; ++i) {
+            memset(&host_out[i], 0, sizeof(sift_b200_keypoint));
+            host_out[i].x = tmp[i].x; host_out[i].y = tmp[i].y;
+            host_out[i].octave = tmp[i].octave; host_out[i].layer = tmp[i].layer;
+            host_out[i].size = tmp[i].size; host_out[i].pori = tmp[i].pori;
+        }
+    }
+    return SIFT_B200_OK;
+}
+
+long sift_b200_launch_count(const sift_b200_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+// Shared device/host definitions for the B200 SIFT engine (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+constexpr int kLayers = 6;      // Gaussian images per octave (intervals + 3, sift.cpp:144)
+constexpr int kDogs = 5;        // DoG images per octave (intervals + 2, sift.cpp:212)
+constexpr int kMaxOctaves = 16;
+constexpr int kMaxRadius = 16;  // largest blur half-width this build instantiates
+constexpr int kOriBins = 36;    // sift.hh:69
+constexpr double kTwoPi = 6.283185307179586;  // M_PI2, sift.hh:5
+constexpr double kPi = 3.14159265358979323846;
+constexpr float kFix = 4294967296.0f;           // 2^32 fixed-point scale for deterministic sums
+constexpr double kUnfix = 1.0 / 4294967296.0;
+
+// One octave of the scale space in HBM.  Every plane is FP32, row-major, `pitch` floats per row
+// (pitch is a multiple of 32 floats = 128 B so that rows are 16-byte aligned for vector loads).
+struct OctaveDesc {
+    int w, h, pitch;
+    float* G[kLayers];  // G[0] is the octave base (sift.cpp:165)
+    float* D[kDogs];    // D[i] = G[i+1] - G[i] (sift.cpp:217)
+};
+
+struct PyramidDesc {
+    int octaves;
+    OctaveDesc oct[kMaxOctaves];
+};
+
+// A scale-space extremum candidate (sift.cpp:14 "Extrema" tuple).
+struct Cand {
+    int x, y, z, o;
+};
+
+// The non-descriptor part of the reference's Keypoint (sift.hh:15-21), 40 bytes.
+struct KpCore {
+    double x, y;
+    int octave, layer;
+    double size, pori;
+};
+
+struct BlurTaps {
+    int radius;
+    float w[kMaxRadius + 1];  // normalised half kernel: w[0] centre, w[u] = tap at distance u
+};
+
+// Device-side counters of one detect call.
+struct Counters {
+    int n_extrema;
+    int n_raw;
+    int n_oriented;
+    int n_final;
+    int overflow;  // bit 0 extrema, bit 1 raw, bit 2 oriented
+    int pad[3];
+};
+
+// Parameters of the per-keypoint stages, all FP64 like the reference's scalars.
+struct StageParams {
+    int doubled;
+    int intervals;
+    int dog_threshold;        // floor(0.5*ct/intervals*255) squeezed into an int (sift.cpp:266,305)
+    double init_sigma;
+    double contrast_threshold;
+    double eigen_ratio;
+    double peak_ratio;
+    double ori_sigma_factor;
+    double desc_scale_factor;
+    int cap_extrema, cap_raw, cap_oriented;
+};
+
+}  // namespace sb

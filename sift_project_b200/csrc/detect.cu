@@ -1,0 +1,549 @@
+// Keypoint kernels (sm_100a): 3x3x3 DoG extrema + compaction, quadratic refinement, orientation
+// histograms, canonical sort + de-duplication, 4x4x8 descriptors.
+//
+// Per-pixel / per-sample arithmetic is FP32 on the FP32 pyramid; every per-keypoint scalar
+// (refinement, scale, radius, peak interpolation, final normalisation) is FP64 and follows the
+// reference's formulas.  Histogram accumulation uses 2^-32 fixed-point integer atomics so that
+// results are independent of the order in which lanes arrive: the whole detect call is
+// bit-reproducible although list compaction uses atomics (the final order is re-established by an
+// exact sort on the reference's own comparison key).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sb {
+
+namespace {
+
+__device__ __forceinline__ float ldg(const float* p) { return __ldg(p); }
+
+// ------------------------------------------------------------------------------------------
+// Extrema scan -- sift.cpp:264-291 (detect_octave_extrema) + :227-256 (is_extremum).
+// A pixel is kept iff |D| > threshold and it is >= all 26 neighbours or <= all of them (ties do
+// not disqualify).  "v >= every neighbour" is evaluated as "v == max over the 27-cell cube".
+// One warp walks a 30-column strip downwards: each lane loads only its own column, the 3-wide
+// row min/max come from warp shuffles, the 3-tall window lives in registers.
+// ------------------------------------------------------------------------------------------
+constexpr int EX_ROWS = 16;  // output rows per warp
+
+__global__ void __launch_bounds__(256)
+k_extrema(const OctaveDesc oct, int octave, float thr, Cand* __restrict__ cands, int cap,
+          Counters* __restrict__ counters) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = oct.w, h = oct.h, pitch = oct.pitch;
+    const int x = blockIdx.x * 30 + lane;                       // lanes 1..30 produce output
+    const int ys = 1 + (blockIdx.y * 8 + warp) * EX_ROWS;       // first output row of this warp
+    if (ys > h - 2) return;
+    const int xc = min(x, w - 1);
+    const bool lane_out = lane >= 1 && lane <= 30 && x <= w - 2;
+
+    float hmin[kDogs][3], hmax[kDogs][3], ctr[kDogs][3];
+    auto load_row = [&](int y, int slot) {
+        const int yc = min(y, h - 1);
+#pragma unroll
+        for (int z = 0; z < kDogs; ++z) {
+            const float v = ldg(oct.D[z] + (size_t)yc * pitch + xc);
+            const float l = __shfl_up_sync(0xffffffffu, v, 1), r = __shfl_down_sync(0xffffffffu, v, 1);
+            hmin[z][slot] = fminf(v, fminf(l, r));
+            hmax[z][slot] = fmaxf(v, fmaxf(l, r));
+            ctr[z][slot] = v;
+        }
+    };
+    load_row(ys - 1, 0);
+    load_row(ys, 1);
+#pragma unroll 1
+    for (int k = 0; k < EX_ROWS; ++k) {
+        const int y = ys + k;
+        if (y > h - 2) break;
+        load_row(y + 1, 2);
+        float vmin[kDogs], vmax[kDogs];
+#pragma unroll
+        for (int z = 0; z < kDogs; ++z) {
+            vmin[z] = fminf(hmin[z][0], fminf(hmin[z][1], hmin[z][2]));
+            vmax[z] = fmaxf(hmax[z][0], fmaxf(hmax[z][1], hmax[z][2]));
+        }
+#pragma unroll
+        for (int z = 1; z <= 3; ++z) {
+            const float c = ctr[z][1];
+            const float mx = fmaxf(vmax[z - 1], fmaxf(vmax[z], vmax[z + 1]));
+            const float mn = fminf(vmin[z - 1], fminf(vmin[z], vmin[z + 1]));
+            const bool hit = lane_out && fabsf(c) > thr && (c == mx || c == mn);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&counters->n_extrema, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (hit) {
+                    const int slot = base + __popc(m & ((1u << lane) - 1));
+                    if (slot < cap) cands[slot] = Cand{x, y, z, octave};
+                }
+            }
+        }
+#pragma unroll
+        for (int z = 0; z < kDogs; ++z) {
+            hmin[z][0] = hmin[z][1]; hmin[z][1] = hmin[z][2];
+            hmax[z][0] = hmax[z][1]; hmax[z][1] = hmax[z][2];
+            ctr[z][0] = ctr[z][1]; ctr[z][1] = ctr[z][2];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Refinement -- sift.cpp:330-436 (compute_keypoints) with get_pixel_cube :32-44,
+// compute_gradient :49-55, compute_hessian :60-80, fit_quadratic :86-106.  FP64, one thread per
+// candidate; cube indexed [z][x][y] of D/255 like the reference.
+// ------------------------------------------------------------------------------------------
+struct Fit {
+    double off[3], g[3], hxx, hyy, hxy, centre;
+};
+
+__device__ Fit fit_cell(const OctaveDesc& oc, int x, int y, int z) {
+    double c[3][3][3];
+#pragma unroll
+    for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+                c[dz][dx][dy] =
+                    (double)ldg(oc.D[z + dz - 1] + (size_t)(y + dy - 1) * oc.pitch + (x + dx - 1)) / 255.0;
+    Fit f;
+    f.centre = c[1][1][1];
+    f.g[0] = 0.5 * (c[2][1][1] - c[0][1][1]);
+    f.g[1] = 0.5 * (c[1][2][1] - c[1][0][1]);
+    f.g[2] = 0.5 * (c[1][1][2] - c[1][1][0]);
+    const double h00 = c[0][1][1] - 2 * c[1][1][1] + c[2][1][1];
+    const double h11 = c[1][0][1] - 2 * c[1][1][1] + c[1][2][1];
+    const double h22 = c[1][1][0] - 2 * c[1][1][1] + c[1][1][2];
+    const double h01 = 0.25 * (c[2][2][1] - c[2][0][1] - c[0][2][1] + c[0][0][1]);
+    const double h02 = 0.25 * (c[2][1][2] - c[2][1][0] - c[0][1][2] + c[0][1][0]);
+    const double h12 = 0.25 * (c[1][0][0] - c[1][2][0] - c[1][0][2] + c[1][2][2]);
+    const double det = h00 * h11 * h22 + 2 * (h01 * h12 * h02) - h02 * h11 * h02 - h00 * h12 * h12 -
+                       h01 * h01 * h22;
+    const double i00 = (h11 * h22 - h12 * h12) / det;
+    const double i01 = (h02 * h12 - h01 * h22) / det;
+    const double i02 = (h01 * h12 - h02 * h11) / det;
+    const double i11 = (h00 * h22 - h02 * h02) / det;
+    const double i12 = (h02 * h01 - h00 * h12) / det;
+    const double i22 = (h00 * h11 - h01 * h01) / det;
+    f.off[0] = -i00 * f.g[0] - i01 * f.g[1] - i02 * f.g[2];
+    f.off[1] = -i01 * f.g[0] - i11 * f.g[1] - i12 * f.g[2];
+    f.off[2] = -i02 * f.g[0] - i12 * f.g[1] - i22 * f.g[2];
+    f.hxx = h11; f.hyy = h22; f.hxy = h12;
+    return f;
+}
+
+__global__ void __launch_bounds__(128)
+k_refine(const PyramidDesc* __restrict__ pyr, const Cand* __restrict__ cands, KpCore* __restrict__ raw,
+         Counters* __restrict__ counters, const StageParams sp) {
+    const int n = min(counters->n_extrema, sp.cap_extrema);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Cand e = cands[i];
+        const OctaveDesc& oc = pyr->oct[e.o];
+        int x = e.x, y = e.y, layer = e.z;
+        Fit f;
+        bool keep = false;
+        for (int step = 0; step < 5; ++step) {  // MAX_CONVERGENCE_STEPS, sift.hh:7
+            f = fit_cell(oc, x, y, layer);
+            const double m = fmax(fabs(f.off[0]), fmax(fabs(f.off[1]), fabs(f.off[2])));
+            if (m < 0.5) {  // CONVERGENCE_THR, sift.hh:8
+                const double dot = f.g[0] * f.off[0] + f.g[1] * f.off[1] + f.g[2] * f.off[2];
+                const double val = f.centre + 0.5 * dot;
+                if (!((fabs(val) * sp.intervals) >= sp.contrast_threshold)) break;
+                const double tr = f.hxx + f.hyy;
+                const double det = f.hxx * f.hyy - f.hxy * f.hxy;
+                if (tr <= 0) break;  // sift.cpp:385 -- rejects every DoG maximum, kept as is
+                const double r = sp.eigen_ratio;
+                keep = !((tr * tr * r) >= ((r + 1) * (r + 1) * det));
+                break;
+            }
+            // a singular Hessian gives inf/NaN offsets; the reference then walks out of range
+            if (!(isfinite(f.off[0]) && isfinite(f.off[1]) && isfinite(f.off[2]))) break;
+            layer += (int)round(f.off[0]);
+            x += (int)round(f.off[1]);
+            y += (int)round(f.off[2]);
+            if (x < 1 || x >= oc.w - 1 || y < 1 || y >= oc.h - 1 || layer < 1 || layer >= kDogs - 1) break;
+        }
+        if (!keep) continue;
+        const double s = (double)(1 << e.o);  // pow(2, octave)
+        KpCore kp;
+        kp.octave = e.o;
+        kp.layer = layer;
+        kp.x = s * ((double)x + f.off[1]);
+        kp.y = s * ((double)y + f.off[2]);
+        kp.size = sp.init_sigma * s * pow(2.0, ((double)layer + f.off[0]) / sp.intervals);
+        kp.pori = 0.0;
+        const int slot = atomicAdd(&counters->n_raw, 1);
+        if (slot < sp.cap_raw) raw[slot] = kp;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Orientation -- sift.cpp:447-533.  One warp per raw keypoint; lanes stride over the
+// (2r+1)^2 window; 36-bin histogram in shared memory (fixed point); lane 0 smooths in place
+// (sequentially, exactly like the reference) and emits one keypoint per qualifying peak.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, KpCore* __restrict__ oriented,
+         Counters* __restrict__ counters, const StageParams sp) {
+    __shared__ unsigned long long s_hist[8][kOriBins];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = min(counters->n_raw, sp.cap_raw);
+    unsigned long long* hist = s_hist[warp];
+    for (int i = blockIdx.x * 8 + warp; i < n; i += gridDim.x * 8) {
+        const KpCore kp = raw[i];
+        const OctaveDesc& oc = pyr->oct[kp.octave];
+        const float* __restrict__ img = oc.G[kp.layer];
+        const int W = oc.w, H = oc.h, pitch = oc.pitch;
+        const double inv = 1.0 / (double)(1 << kp.octave);
+        const int x = (int)round(kp.x * inv), y = (int)round(kp.y * inv);
+        const double scale = sp.ori_sigma_factor * (kp.size * inv);
+        const int radius = (int)round(3.0 * scale);
+        const float neg_inv_denom = (float)(-1.0 / (2.0 * scale * scale));
+        for (int b = lane; b < kOriBins; b += 32) hist[b] = 0ull;
+        __syncwarp();
+        const int side = 2 * radius + 1;
+        const int total = side * side;
+        for (int s = lane; s < total; s += 32) {
+            const int jr = s / side;             // row of the window -> y offset
+            const int i_off = s - jr * side - radius;
+            const int j_off = jr - radius;
+            const int px = x + i_off, py = y + j_off;
+            if (px - 1 < 0 || px + 1 >= W || py - 1 < 0 || py + 1 >= H) continue;
+            const float* c = img + (size_t)py * pitch + px;
+            const float dx = ldg(c + 1) - ldg(c - 1);
+            const float dy = ldg(c - pitch) - ldg(c + pitch);  // up minus down, sift.cpp:483
+            const float mag = sqrtf(dx * dx + dy * dy);
+            const float ang = atan2f(dy, dx);
+            const float wgt = __expf((float)(i_off * i_off + j_off * j_off) * neg_inv_denom);
+            int b = (int)roundf((float)kOriBins * (ang + 3.14159265358979323846f) * (1.0f / 6.283185307179586f));
+            b = (b < kOriBins) ? b : 0;  // sift.cpp:489-490: bin 0 <-> angle -pi
+            b = max(b, 0);
+            const long long fx = __float2ll_rn(wgt * mag * kFix);
+            atomicAdd(&hist[b], (unsigned long long)fx);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double hd[kOriBins];
+            for (int b = 0; b < kOriBins; ++b) hd[b] = (double)(long long)hist[b] * kUnfix;
+            for (int it = 0; it < 2; ++it)  // ORI_SMOOTH_ITERATIONS; in place, sequential
+                for (int b = 0; b < kOriBins; ++b)
+                    hd[b] = 0.25 * hd[(b - 1 + kOriBins) % kOriBins] + 0.5 * hd[b] +
+                            0.25 * hd[(b + 1) % kOriBins];
+            double top = hd[0];
+            for (int b = 1; b < kOriBins; ++b) top = fmax(top, hd[b]);
+            for (int b = 0; b < kOriBins; ++b) {
+                const double h0 = hd[(b - 1 + kOriBins) % kOriBins], h1 = hd[b], h2 = hd[(b + 1) % kOriBins];
+                if (!(h1 > h0 && h1 > h2 && h1 > (sp.peak_ratio * top))) continue;
+                double pos = b + 0.5 * (h0 - h2) / (h0 - 2 * h1 + h2);
+                pos = fmod(pos + kOriBins, (double)kOriBins);
+                double ori = kTwoPi * pos / kOriBins;
+                ori = fmod(ori + kTwoPi, kTwoPi);
+                KpCore out = kp;
+                out.pori = ori;
+                if (sp.doubled) { out.x /= 2; out.y /= 2; out.size /= 2; }
+                const int slot = atomicAdd(&counters->n_oriented, 1);
+                if (slot < sp.cap_oriented) oriented[slot] = out;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Canonical order + de-duplication -- clean_keypoints, sift.cpp:20-24 with Keypoint::operator<
+// and operator== (sift.hh:25-41).  Counting sort on floor(x) buckets, exact ranking inside each
+// bucket with the reference's comparator, equal records collapse to the first.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool kp_less(const KpCore& a, const KpCore& b) {
+    if (a.x != b.x) return a.x < b.x;
+    if (a.y != b.y) return a.y < b.y;
+    if (a.size != b.size) return a.size > b.size;
+    if (a.pori != b.pori) return a.pori < b.pori;
+    return a.octave > b.octave;
+}
+__device__ __forceinline__ bool kp_same(const KpCore& a, const KpCore& b) {
+    return a.x == b.x && a.y == b.y && a.size == b.size && a.pori == b.pori;
+}
+__device__ __forceinline__ int bucket_of(double x, int nb) {
+    int b = (int)floor(x);
+    return min(max(b, 0), nb - 1);
+}
+
+__global__ void k_sort_clear(SortScratch ss) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= ss.nb; i += gridDim.x * blockDim.x) {
+        ss.bucket_cnt[i] = 0;
+        ss.uniq_cnt[i] = 0;
+        if (i < ss.nb) ss.bucket_fill[i] = 0;
+    }
+}
+
+__global__ void k_bucket_count(const KpCore* __restrict__ kps, const Counters* __restrict__ counters,
+                               SortScratch ss, int cap) {
+    const int n = min(counters->n_oriented, cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&ss.bucket_cnt[bucket_of(kps[i].x, ss.nb)], 1);
+}
+
+// single-CTA exclusive scan of cnt[0..n) into off[0..n], off[n] = total
+__global__ void __launch_bounds__(1024) k_scan(const int* __restrict__ cnt, int* __restrict__ off, int n,
+                                               int* __restrict__ total_out) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = (i < n) ? cnt[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int wv = s_warp[lane];
+            int winc = wv;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, winc, d);
+                if (lane >= d) winc += t;
+            }
+            s_warp[lane] = winc - wv;  // exclusive prefix of warp totals
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        if (i < n) off[i] = carry + s_warp[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[31] + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        off[n] = s_carry;
+        if (total_out) *total_out = s_carry;
+    }
+}
+
+__global__ void k_bucket_scatter(const KpCore* __restrict__ kps, const Counters* __restrict__ counters,
+                                 SortScratch ss, int cap) {
+    const int n = min(counters->n_oriented, cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int b = bucket_of(kps[i].x, ss.nb);
+        ss.perm[ss.bucket_off[b] + atomicAdd(&ss.bucket_fill[b], 1)] = i;
+    }
+}
+
+// one warp per bucket: exact rank inside the bucket, duplicates dropped, survivors compacted to
+// the front of the bucket's range in `sorted`.
+__global__ void __launch_bounds__(256) k_bucket_rank(const KpCore* __restrict__ kps, SortScratch ss) {
+    const int lane = threadIdx.x & 31;
+    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < ss.nb; b += (gridDim.x * blockDim.x) >> 5) {
+        const int s = ss.bucket_off[b], e = ss.bucket_off[b + 1];
+        if (e == s) continue;
+        for (int p = s + lane; p < e; p += 32) {
+            const int ip = ss.perm[p];
+            const KpCore a = kps[ip];
+            int rank = 0, dup = 0;
+            for (int q = s; q < e; ++q) {
+                if (q == p) continue;
+                const int iq = ss.perm[q];
+                const KpCore c = kps[iq];
+                const bool lt = kp_less(c, a), gt = kp_less(a, c);
+                const bool before = lt || (!gt && iq < ip);
+                rank += before ? 1 : 0;
+                if (before && kp_same(c, a)) dup = 1;
+            }
+            ss.tmp_sorted[s + rank] = ip | (dup << 30);
+        }
+        __syncwarp();
+        int kept = 0;
+        for (int t = s; t < e; t += 32) {
+            const int p = t + lane;
+            int v = 0;
+            bool keep = false;
+            if (p < e) { v = ss.tmp_sorted[p]; keep = !((v >> 30) & 1); }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) ss.sorted[s + kept + __popc(m & ((1u << lane) - 1))] = v & 0x3fffffff;
+            kept += __popc(m);
+        }
+        if (lane == 0) ss.uniq_cnt[b] = kept;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bucket_gather(SortScratch ss) {
+    const int lane = threadIdx.x & 31;
+    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < ss.nb; b += (gridDim.x * blockDim.x) >> 5) {
+        const int s = ss.bucket_off[b], u = ss.uniq_cnt[b], o = ss.uniq_off[b];
+        for (int k = lane; k < u; k += 32) ss.final_order[o + k] = ss.sorted[s + k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Descriptors -- sift.cpp:610-682 (compute_descriptors), :541-571 (update_histogram, trilinear),
+// :576-603 (convert_hist_to_desc).  One warp per final keypoint, lanes stride over the rotated
+// (2r+1)^2 window, 4x4x8 fixed-point histogram in shared memory, FP64 normalise / clamp 0.2 /
+// renormalise / floor(512 x) / min 255.  Writes the 168-byte record and the dense 128-byte row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ oriented,
+           const int* __restrict__ final_order, const Counters* __restrict__ counters,
+           uint8_t* __restrict__ records, uint8_t* __restrict__ desc, int cap_final, const StageParams sp) {
+    __shared__ unsigned long long s_hist[8][128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long* hist = s_hist[warp];
+    const int n = min(counters->n_final, cap_final);
+    for (int i = blockIdx.x * 8 + warp; i < n; i += gridDim.x * 8) {
+        const KpCore kp = oriented[final_order[i]];
+        const OctaveDesc& oc = pyr->oct[kp.octave];
+        const float* __restrict__ img = oc.G[kp.layer];
+        const int W = oc.w, H = oc.h, pitch = oc.pitch;
+        const double inv = sp.doubled ? (kp.octave >= 1 ? 1.0 / (double)(1 << (kp.octave - 1)) : 2.0)
+                                      : 1.0 / (double)(1 << kp.octave);
+        const int x = (int)(kp.x * inv), y = (int)(kp.y * inv);  // truncation, sift.cpp:623-624
+        const double size = kp.size * inv;
+        const double hw = sp.desc_scale_factor * size;
+        const double tmp_r = round(hw * 0.5 * sqrt(2.0) * (4 + 1.0) + 0.5);
+        const int radius = (int)fmin(tmp_r, sqrt((double)(W * W + H * H)));
+        const float ca = (float)cos(kp.pori), sa = (float)sin(kp.pori);
+        const float inv_hw = (float)(1.0 / hw);
+        const float pori = (float)kp.pori;
+        for (int b = lane; b < 128; b += 32) hist[b] = 0ull;
+        __syncwarp();
+        const int side = 2 * radius + 1;
+        const int total = side * side;
+        for (int s = lane; s < total; s += 32) {
+            const int rr_i = s / side;
+            const int col = s - rr_i * side - radius;
+            const int row = rr_i - radius;
+            const float rr = ((float)col * sa + (float)row * ca) * inv_hw;
+            const float cr = ((float)col * ca - (float)row * sa) * inv_hw;
+            const float rb = rr + 1.5f, cb = cr + 1.5f;  // + DESC_HIST_WIDTH/2 - 0.5 (integer 4/2)
+            if (!(rb > -1.0f && rb < 4.0f && cb > -1.0f && cb < 4.0f)) continue;
+            const int ny = row + y, nx = col + x;
+            if (!(nx > 0 && nx < W - 1 && ny > 0 && ny < H - 1)) continue;
+            const float* c = img + (size_t)ny * pitch + nx;
+            const float dx = ldg(c + 1) - ldg(c - 1);
+            const float dy = ldg(c - pitch) - ldg(c + pitch);
+            const float mag = sqrtf(dx * dx + dy * dy);
+            float ang = atan2f(dy, dx) - pori;  // in (-3pi, pi]
+            ang -= 6.283185307179586f * floorf(ang * (1.0f / 6.283185307179586f));
+            if (ang < 0.f) ang = 0.f;
+            if (ang >= 6.283185307179586f) ang -= 6.283185307179586f;
+            const float ob = ang * (8.0f / 6.283185307179586f);
+            const float wgt = __expf(-(rr * rr + cr * cr) * 0.125f);
+            const float m = mag * wgt;
+            const float fbr = floorf(rb), fbc = floorf(cb), fbo = floorf(ob);
+            const int br = (int)fbr, bc = (int)fbc, bo = (int)fbo;
+            const float fr = rb - fbr, fc = cb - fbc, fo = ob - fbo;
+#pragma unroll
+            for (int a = 0; a <= 1; ++a) {
+                const int ri = br + a;
+                if (ri < 0 || ri >= 4) continue;
+                const float vr = m * (a == 0 ? 1.0f - fr : fr);
+#pragma unroll
+                for (int bq = 0; bq <= 1; ++bq) {
+                    const int ci = bc + bq;
+                    if (ci < 0 || ci >= 4) continue;
+                    const float vc = vr * (bq == 0 ? 1.0f - fc : fc);
+#pragma unroll
+                    for (int d = 0; d <= 1; ++d) {
+                        const int oi = (bo + d) & 7;
+                        const float vo = vc * (d == 0 ? 1.0f - fo : fo);
+                        atomicAdd(&hist[(ri * 4 + ci) * 8 + oi], (unsigned long long)__float2ll_rn(vo * kFix));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // lane L owns bins 4L..4L+3 (consecutive bytes of the descriptor)
+        double hv[4];
+        double ss = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            hv[k] = (double)(long long)hist[4 * lane + k] * kUnfix;
+            ss += hv[k] * hv[k];
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+        double inv_n = 1.0 / sqrt(ss);
+        ss = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            hv[k] *= inv_n;
+            if (hv[k] > 0.2) hv[k] = 0.2;  // DESC_MAGNITUDE_THR
+            ss += hv[k] * hv[k];
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+        inv_n = 1.0 / sqrt(ss);
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int q = (int)floor(512.0 * hv[k] * inv_n);  // INT_DESCR_FCTR
+            q = min(q, 255);
+            q = max(q, 0);  // NaN (empty histogram) -> 0; the reference's cast of NaN is undefined
+            packed |= (uint32_t)q << (8 * k);
+        }
+        uint8_t* rec = records + (size_t)i * 168;
+        *reinterpret_cast<uint32_t*>(rec + 40 + 4 * lane) = packed;
+        *reinterpret_cast<uint32_t*>(desc + (size_t)i * 128 + 4 * lane) = packed;
+        if (lane == 0) {
+            *reinterpret_cast<double*>(rec + 0) = kp.x;
+            *reinterpret_cast<double*>(rec + 8) = kp.y;
+            *reinterpret_cast<int*>(rec + 16) = kp.octave;
+            *reinterpret_cast<int*>(rec + 20) = kp.layer;
+            *reinterpret_cast<double*>(rec + 24) = kp.size;
+            *reinterpret_cast<double*>(rec + 32) = kp.pori;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int threshold, Cand* cands, int cap,
+                           Counters* counters, cudaStream_t s) {
+    if (oct.w < 3 || oct.h < 3) return cudaSuccess;
+    dim3 grid((oct.w - 2 + 29) / 30, (oct.h - 2 + 8 * EX_ROWS - 1) / (8 * EX_ROWS));
+    k_extrema<<<grid, 256, 0, s>>>(oct, octave, (float)threshold, cands, cap, counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_refine(const PyramidDesc* d_pyr, const Cand* cands, KpCore* raw, Counters* counters,
+                          const StageParams& sp, cudaStream_t s) {
+    k_refine<<<148 * 4, 128, 0, s>>>(d_pyr, cands, raw, counters, sp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_orient(const PyramidDesc* d_pyr, const KpCore* raw, KpCore* oriented, Counters* counters,
+                          const StageParams& sp, cudaStream_t s) {
+    k_orient<<<148 * 4, 256, 0, s>>>(d_pyr, raw, oriented, counters, sp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sort_dedup(const KpCore* oriented, Counters* counters, const SortScratch& ss,
+                              const StageParams& sp, cudaStream_t s, int* launches) {
+    cudaError_t e;
+    k_sort_clear<<<(ss.nb + 256) / 256, 256, 0, s>>>(ss);
+    k_bucket_count<<<148 * 2, 256, 0, s>>>(oriented, counters, ss, sp.cap_oriented);
+    k_scan<<<1, 1024, 0, s>>>(ss.bucket_cnt, ss.bucket_off, ss.nb, nullptr);
+    k_bucket_scatter<<<148 * 2, 256, 0, s>>>(oriented, counters, ss, sp.cap_oriented);
+    k_bucket_rank<<<148 * 4, 256, 0, s>>>(oriented, ss);
+    k_scan<<<1, 1024, 0, s>>>(ss.uniq_cnt, ss.uniq_off, ss.nb, &counters->n_final);
+    k_bucket_gather<<<148 * 2, 256, 0, s>>>(ss);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (launches) *launches += 7;
+    return cudaSuccess;
+}
+
+cudaError_t launch_describe(const PyramidDesc* d_pyr, const KpCore* oriented, const int* final_order,
+                            Counters* counters, uint8_t* records, uint8_t* desc, int cap_final,
+                            const StageParams& sp, cudaStream_t s) {
+    k_describe<<<148 * 4, 256, 0, s>>>(d_pyr, oriented, final_order, counters, records, desc, cap_final, sp);
+    return cudaGetLastError();
+}
+
+}  // namespace sb

@@ -1,0 +1,64 @@
+// Host-callable launchers of the sm_100a kernels (internal to libsift_b200.so).
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+// pyramid.cu
+cudaError_t pyramid_init();
+cudaError_t launch_prepare_u8(const uint8_t* src, int sw, int sh, int ch, float* dst, int dw, int dh,
+                              int dpitch, int doubled, cudaStream_t s);
+cudaError_t launch_prepare_f32(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh,
+                               int dpitch, int doubled, cudaStream_t s);
+cudaError_t launch_blur(const float* in, float* out, float* dog, float* dec, int w, int h, int pitch,
+                        int dec_w, int dec_h, int dec_pitch, const BlurTaps& taps, cudaStream_t s);
+
+// detect.cu
+struct SortScratch {
+    int nb;             // number of x buckets (= output-frame image width)
+    int* bucket_cnt;    // [nb + 1]
+    int* bucket_off;    // [nb + 1]
+    int* bucket_fill;   // [nb]
+    int* uniq_cnt;      // [nb + 1]
+    int* uniq_off;      // [nb + 1]
+    int* perm;          // [cap_oriented]
+    int* tmp_sorted;    // [cap_oriented]
+    int* sorted;        // [cap_oriented]
+    int* final_order;   // [cap_oriented]
+};
+cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int threshold, Cand* cands, int cap,
+                           Counters* counters, cudaStream_t s);
+cudaError_t launch_refine(const PyramidDesc* d_pyr, const Cand* cands, KpCore* raw,
+                          Counters* counters, const StageParams& sp, cudaStream_t s);
+cudaError_t launch_orient(const PyramidDesc* d_pyr, const KpCore* raw, KpCore* oriented,
+                          Counters* counters, const StageParams& sp, cudaStream_t s);
+cudaError_t launch_sort_dedup(const KpCore* oriented, Counters* counters, const SortScratch& ss,
+                              const StageParams& sp, cudaStream_t s, int* launches);
+cudaError_t launch_describe(const PyramidDesc* d_pyr, const KpCore* oriented, const int* final_order,
+                            Counters* counters, uint8_t* records, uint8_t* desc, int cap_final,
+                            const StageParams& sp, cudaStream_t s);
+
+// match_simt.cu
+struct MatchScratch {
+    int* part_idx;   // [splits][na]
+    int* part_d1;
+    int* part_d2;
+    int* norms_a;    // [na]
+    int* norms_b;    // [nb]
+    size_t cap_rows; // rows of A the partial buffers were sized for (x max splits)
+    int max_splits;
+};
+cudaError_t launch_norms(const uint8_t* d, int n, int* norms, cudaStream_t s);
+cudaError_t launch_match_simt(const uint8_t* a, int na, const uint8_t* b, int nb, int* best_idx,
+                              int* best_d2, int* second_d2, const MatchScratch& ms, int sm_count,
+                              cudaStream_t s, int* launches);
+// match.cu: picks the tcgen05 kernel (match_tc.cu) for large problems, else the SIMT kernel
+cudaError_t match_init();
+bool match_uses_tensor_cores(int na, int nb);
+cudaError_t launch_match(const uint8_t* a, int na, const uint8_t* b, int nb, int* best_idx, int* best_d2,
+                         int* second_d2, const MatchScratch& ms, int sm_count, cudaStream_t s, int* launches);
+cudaError_t launch_match_emit(const int* best_idx, const int* best_d2, const int* second_d2, int na,
+                              int nb, double ratio, int* out_ia, int* out_ib, double* out_dist,
+                              int cap, int* out_count, cudaStream_t s);
+
+}  // namespace sb

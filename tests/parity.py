@@ -1,0 +1,65 @@
+"""Comparison helpers implementing BASELINE.json's parity criteria (test infrastructure)."""
+import numpy as np
+from scipy.spatial import cKDTree
+
+POS_TOL = 0.01      # px           (north_star: 0.01 px)
+SIZE_RTOL = 1e-3    # relative     (north_star: 1e-3 relative sigma)
+ORI_TOL = 0.02      # rad, used only to pair up the several orientations of one location
+
+
+def pair_keypoints(got, want, pos_tol=POS_TOL, size_rtol=SIZE_RTOL, ori_tol=ORI_TOL, use_ori=True):
+    """Greedy one-to-one pairing of two record arrays.  Returns (idx_got, idx_want)."""
+    if len(got) == 0 or len(want) == 0:
+        return np.zeros(0, int), np.zeros(0, int)
+    tree = cKDTree(np.stack([want["x"], want["y"]], 1))
+    used = np.zeros(len(want), bool)
+    gi, wi = [], []
+    cands = tree.query_ball_point(np.stack([got["x"], got["y"]], 1), pos_tol * np.sqrt(2.0))
+    for i, cs in enumerate(cands):
+        best, best_d = -1, 1e9
+        for j in cs:
+            if used[j]:
+                continue
+            if abs(got["x"][i] - want["x"][j]) > pos_tol or abs(got["y"][i] - want["y"][j]) > pos_tol:
+                continue
+            if abs(got["size"][i] - want["size"][j]) > size_rtol * want["size"][j]:
+                continue
+            if got["octave"][i] != want["octave"][j] or got["layer"][i] != want["layer"][j]:
+                continue
+            d = 0.0
+            if use_ori:
+                d = abs((got["pori"][i] - want["pori"][j] + np.pi) % (2 * np.pi) - np.pi)
+                if d > ori_tol:
+                    continue
+            if d < best_d:
+                best, best_d = j, d
+        if best >= 0:
+            used[best] = True
+            gi.append(i)
+            wi.append(best)
+    return np.array(gi, int), np.array(wi, int)
+
+
+def recall_precision(got, want, **kw):
+    gi, wi = pair_keypoints(got, want, **kw)
+    rec = len(wi) / max(len(want), 1)
+    prec = len(gi) / max(len(got), 1)
+    return rec, prec, gi, wi
+
+
+def descriptor_report(got, want, gi, wi):
+    """Per paired keypoint: max |desc difference| in quantised levels."""
+    if len(gi) == 0:
+        return dict(n=0, frac_le1=1.0, frac_exact=1.0, max=0, mean_abs=0.0)
+    d = np.abs(got["desc"][gi].astype(np.int16) - want["desc"][wi].astype(np.int16))
+    mx = d.max(1)
+    return dict(n=len(gi), frac_le1=float((mx <= 1).mean()), frac_exact=float((mx == 0).mean()),
+                frac_le2=float((mx <= 2).mean()), max=int(mx.max()), mean_abs=float(d.mean()),
+                p999=float(np.quantile(mx, 0.999)))
+
+
+def set_diff_report(a, b):
+    """Rows of two integer arrays as sets: (|a & b|, |a - b|, |b - a|)."""
+    sa = {tuple(r) for r in np.asarray(a).tolist()}
+    sb = {tuple(r) for r in np.asarray(b).tolist()}
+    return len(sa & sb), len(sa - sb), len(sb - sa)

@@ -1,0 +1,261 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes binding), against the CPU
+oracle on the same inputs and against the golden vectors the real reference produced.
+
+Criteria (BASELINE.json north_star): keypoint recall / precision >= 99.5 % at 0.01 px and 1e-3
+relative size; descriptors within 1 quantisation level; match index lists identical."""
+import json
+import os
+
+import numpy as np
+import pytest
+from PIL import Image
+
+import parity as P
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+S = pytest.importorskip("sift_project_b200")
+REPORT = {}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = S.SiftContext(1024, 768)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def synth(golden_dir):
+    return np.load(os.path.join(golden_dir, "synth_256x192.npz"))
+
+
+@pytest.fixture(scope="module")
+def config1(golden_dir):
+    return np.load(os.path.join(golden_dir, "config1.npz"))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _dump_report():
+    yield
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_report.json", "w") as f:
+        json.dump(REPORT, f, indent=1, default=float)
+    print("\nPARITY REPORT", json.dumps(REPORT, default=float))
+
+
+def test_pyramid_planes_match_oracle(ctx, synth):
+    """Every Gaussian and DoG plane of every octave vs the FP64 oracle (image.cpp:156-238,
+    sift.cpp:161-225).  FP32 storage: a few ulp of 255."""
+    img = synth["image"]
+    ctx.detect(img)
+    run = O.Run(O.port(), img, keep_pyramid=True)
+    st = ctx.stats()
+    assert st["octaves"] == run.octaves == 7
+    worst_g = worst_d = 0.0
+    for o in range(run.octaves):
+        assert ctx.plane_dims(o) == run.dims(o)
+        for l in range(6):
+            worst_g = max(worst_g, np.abs(ctx.gaussian(o, l) - run.gaussian(o, l)).max())
+        for l in range(5):
+            worst_d = max(worst_d, np.abs(ctx.dog(o, l) - run.dog(o, l)).max())
+    REPORT["pyramid_max_abs_err"] = dict(gaussian=worst_g, dog=worst_d)
+    assert worst_g < 2e-4 and worst_d < 2e-4
+    # golden planes from the real reference
+    assert np.abs(ctx.gaussian(1, 3) - synth["g_o1_l3"]).max() < 2e-4
+    assert np.abs(ctx.dog(1, 2) - synth["dog_o1_l2"]).max() < 2e-4
+
+
+def test_stage_lists_match_reference_golden(ctx, synth):
+    """Extrema, refined and oriented keypoints vs the real reference's golden dump."""
+    img = synth["image"]
+    final = ctx.detect(img)
+    ex = ctx.extrema()
+    both, only_gpu, only_ref = P.set_diff_report(ex, synth["extrema"])
+    REPORT["synth_extrema"] = dict(both=both, only_gpu=only_gpu, only_ref=only_ref)
+    assert only_gpu + only_ref <= max(2, 0.005 * len(synth["extrema"]))
+    for stage, key in ((0, "raw"), (1, "oriented")):
+        got = ctx.stage_keypoints(stage)
+        rec, prec, gi, wi = P.recall_precision(got, synth[key], use_ori=(stage == 1))
+        REPORT[f"synth_{key}"] = dict(n_gpu=len(got), n_ref=len(synth[key]), recall=rec, precision=prec)
+        assert rec >= 0.995 and prec >= 0.995
+    rec, prec, gi, wi = P.recall_precision(final, synth["final"])
+    rep = P.descriptor_report(final, synth["final"], gi, wi)
+    REPORT["synth_final"] = dict(n_gpu=len(final), n_ref=len(synth["final"]), recall=rec, precision=prec, desc=rep)
+    assert rec >= 0.995 and prec >= 0.995
+    assert rep["frac_le1"] >= 0.99
+
+
+def test_output_order_is_the_reference_sort(ctx, synth):
+    """clean_keypoints (sift.cpp:20-24): ascending by Keypoint::operator<, no duplicates."""
+    k = ctx.detect(synth["image"])
+    key = np.stack([k["x"], k["y"], -k["size"], k["pori"], -k["octave"].astype(float)], 1)
+    order = np.lexsort(key.T[::-1])
+    assert np.array_equal(order, np.arange(len(k)))
+    four = np.stack([k["x"], k["y"], k["size"], k["pori"]], 1)
+    assert len(np.unique(four, axis=0)) == len(k)
+
+
+def test_detect_is_bit_reproducible(ctx, synth):
+    a = ctx.detect(synth["image"])
+    b = ctx.detect(synth["image"])
+    assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("name", ["image1", "image2"])
+def test_config1_detect(ctx, config1, golden_dir, name):
+    """stitching/image{1,2}.jpg (stb-decoded, RGB): 1286 / 1430 keypoints in the reference."""
+    px = np.asarray(Image.open(os.path.join(golden_dir, name + ".png")))
+    assert px.ndim == 3 and px.shape[2] == 3
+    got = ctx.detect(px)
+    want = config1[name + "_final"]
+    st = ctx.stats()
+    rec, prec, gi, wi = P.recall_precision(got, want)
+    rep = P.descriptor_report(got, want, gi, wi)
+    REPORT[f"config1_{name}"] = dict(stats=st, n_ref=len(want), recall=rec, precision=prec, desc=rep,
+                                     ref_extrema=len(config1[name + "_extrema"]), ref_raw=len(config1[name + "_raw"]))
+    assert st["octaves"] == 8
+    assert abs(st["extrema"] - len(config1[name + "_extrema"])) <= 0.005 * len(config1[name + "_extrema"])
+    assert rec >= 0.995 and prec >= 0.995
+    assert rep["frac_le1"] >= 0.99
+
+
+def test_config1_match_on_reference_descriptors(ctx, config1):
+    """match_keypoints (sift.cpp:783-815) on the reference's own descriptors: the 269 matches,
+    identical indices and distances."""
+    a, b = config1["image1_final"]["desc"], config1["image2_final"]["desc"]
+    ia, ib, d = ctx.match(a, b)
+    assert len(ia) == 269
+    assert np.array_equal(ia, config1["match_ia"]) and np.array_equal(ib, config1["match_ib"])
+    assert np.array_equal(d, config1["match_dist"])
+
+
+def test_config1_end_to_end_matches(ctx, golden_dir, config1):
+    """detect x2 + match, all on the GPU, vs the reference's match list mapped through the
+    keypoint pairing (ratio margins of config 1 are >= 2.5e-3)."""
+    k = []
+    for name in ("image1", "image2"):
+        k.append(ctx.detect(np.asarray(Image.open(os.path.join(golden_dir, name + ".png")))))
+    ia, ib, d = ctx.match(k[0]["desc"], k[1]["desc"])
+    oa, ob, od = O.match(O.port(), k[0]["desc"], k[1]["desc"])
+    assert np.array_equal(ia, oa) and np.array_equal(ib, ob) and np.array_equal(d, od)
+    g1, w1 = P.pair_keypoints(k[0], config1["image1_final"])
+    g2, w2 = P.pair_keypoints(k[1], config1["image2_final"])
+    m1 = dict(zip(g1.tolist(), w1.tolist()))
+    m2 = dict(zip(g2.tolist(), w2.tolist()))
+    mapped = {(m1.get(int(i), -1), m2.get(int(j), -2)) for i, j in zip(ia, ib)}
+    ref = set(zip(config1["match_ia"].tolist(), config1["match_ib"].tolist()))
+    REPORT["config1_matches"] = dict(gpu=len(ia), ref=len(ref), common=len(mapped & ref))
+    assert len(mapped & ref) >= 0.98 * len(ref)
+
+
+def test_match_known_answers(ctx, golden_dir):
+    """Ties (lowest j wins), duplicate best (never matches), |B| = 0, 1, 2."""
+    k = np.load(os.path.join(golden_dir, "match_kat.npz"))
+    a, b = k["a"], k["b"]
+    cases = {"full": (a, b), "b1": (a[:20], b[:1]), "b0": (a[:20], b[:0]), "a0": (a[:0], b), "b2": (a[:50], b[:2])}
+    for tag, (x, y) in cases.items():
+        ia, ib, d = ctx.match(x, y)
+        assert np.array_equal(ia, k[tag + "_ia"]), tag
+        assert np.array_equal(ib, k[tag + "_ib"]), tag
+        assert np.array_equal(d, k[tag + "_dist"]), tag
+
+
+@pytest.mark.parametrize("na,nb", [(1, 1), (33, 1000), (1000, 33), (2500, 3100), (4096, 4096)])
+def test_match_random_sizes_vs_oracle(ctx, na, nb):
+    a, b = O.synth_descriptors(na, seed=na), O.synth_descriptors(nb, seed=nb + 7)
+    b[nb // 2] = b[0]
+    if na > 3 and nb > 3:
+        b[3] = a[3]
+    ia, ib, d = ctx.match(a, b)
+    oa, ob, od = O.match(O.port(), a, b)
+    assert np.array_equal(ia, oa) and np.array_equal(ib, ob) and np.array_equal(d, od)
+
+
+def test_match_device_resident_top2(ctx):
+    import torch
+    a, b = O.synth_descriptors(777, seed=5), O.synth_descriptors(1500, seed=6)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    idx = torch.empty(len(a), dtype=torch.int32, device="cuda")
+    d1, d2 = torch.empty_like(idx), torch.empty_like(idx)
+    torch.cuda.synchronize()
+    ctx.match_enqueue(ta, len(a), tb, len(b), idx, d1, d2)
+    ctx.sync()
+    D = ((a.astype(np.int64)[:, None, :] - b.astype(np.int64)[None, :, :]) ** 2).sum(-1)
+    order = np.argsort(D, axis=1, kind="stable")
+    r = np.arange(len(a))
+    assert np.array_equal(idx.cpu().numpy(), order[:, 0])
+    assert np.array_equal(d1.cpu().numpy(), D[r, order[:, 0]])
+    assert np.array_equal(d2.cpu().numpy(), D[r, order[:, 1]])
+
+
+def test_undoubled_and_f32_and_rgb_inputs(ctx):
+    """double_image_size = false (sift.cpp:119-126: same sigma), float input, RGB input."""
+    g = O.synth_image(240, 320, seed=3)
+    rng = np.random.default_rng(5)
+    rgb = np.clip(np.stack([g, np.roll(g, 3, 1), np.roll(g, 5, 0)], -1).astype(np.int32)
+                  + rng.integers(-3, 4, (240, 320, 3)), 0, 255).astype(np.uint8)
+    for tag, img, doubled in (("gray_undoubled", g, False), ("rgb_doubled", rgb, True),
+                              ("rgb_undoubled", rgb, False), ("f32_gray", g.astype(np.float32) * 0.5 + 17.25, True)):
+        got = ctx.detect(img, double_image_size=doubled)
+        run = O.Run(O.port(), img, doubled, keep_pyramid=False)
+        want = run.keypoints(2)
+        rec, prec, gi, wi = P.recall_precision(got, want)
+        rep = P.descriptor_report(got, want, gi, wi)
+        REPORT[tag] = dict(n_gpu=len(got), n_ref=len(want), recall=rec, precision=prec, desc=rep)
+        assert len(want) > 50
+        assert rec >= 0.99 and prec >= 0.99, tag
+
+
+def test_max_octaves_extension_filters_octaves(ctx, synth):
+    """Octave o never depends on octaves > o (sift.cpp:187-199): capping = filtering."""
+    full = ctx.detect(synth["image"])
+    capped = ctx.detect(synth["image"], max_octaves=4)
+    want = full[full["octave"] < 4]
+    assert capped.tobytes() == want.tobytes()
+    assert ctx.stats()["octaves"] == 4
+
+
+def test_small_and_odd_sizes(ctx):
+    for h, w in ((2, 2), (3, 5), (7, 9), (17, 33), (64, 31), (129, 257)):
+        img = O.synth_image(max(h, 8), max(w, 8), seed=h * w)[:h, :w]
+        got = ctx.detect(img)
+        run = O.Run(O.port(), img, keep_pyramid=False)
+        want = run.keypoints(2)
+        assert ctx.stats()["octaves"] == run.octaves, (h, w)
+        rec, prec, _, _ = P.recall_precision(got, want)
+        assert len(want) - rec * len(want) <= 1 and len(got) - prec * len(got) <= 1, (h, w)
+
+
+def test_flat_image_has_no_keypoints(ctx):
+    assert len(ctx.detect(np.full((100, 120), 128, np.uint8))) == 0
+    assert ctx.stats()["extrema"] == 0
+
+
+def test_error_behaviour(ctx):
+    img = O.synth_image(64, 64, seed=1)
+    with pytest.raises(S.SiftError) as e:
+        ctx.detect(img, intervals=4)
+    assert e.value.code == 5
+    with pytest.raises(S.SiftError) as e:
+        ctx.detect(np.zeros((64, 64, 2), np.uint8))
+    assert e.value.code == 1
+    with pytest.raises(S.SiftError) as e:
+        ctx.detect(np.zeros((4000, 4000), np.uint8))
+    assert e.value.code == 6
+    with pytest.raises(S.SiftError) as e:
+        ctx.detect(O.synth_image(192, 256, seed=42), capacity=10)
+    assert e.value.code == 4
+
+
+def test_device_resident_enqueue_path(ctx, synth):
+    import torch
+    img = torch.from_numpy(synth["image"]).cuda()
+    torch.cuda.synchronize()
+    ctx.detect_enqueue(img, 256, 192)
+    n = ctx.detect_finish()
+    host = ctx.detect(synth["image"])
+    assert n == len(host)
+    rec, desc, n2 = ctx.result_device()
+    assert n2 == n and rec and desc
