@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""Benchmark of the SIFT hot path (detect + describe) on B200 -- BASELINE.json's metric
+"4K SIFT images/sec (detect+describe)" on config "synthetic 3840x2160 (4K) batch of 256 images
+sharded by image across 1/2/4/8 B200".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            this repo's CUDA path
+  python bench.py --impl reference ...                            the reference's CPU path (oracle/_ref)
+
+One step = one pass of detect+describe over the whole batch (256 images, image i on rank i mod N:
+total work fixed => "strong" scaling).  `value` is timed with the images already in HBM and the
+results left in HBM; `e2e` goes through the host-buffer C-ABI calls (pinned host pixels in,
+168-byte keypoint records out) with both copies inside the timed region.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W4K, H4K = 3840, 2160
+METRIC = "4K SIFT images/sec (detect+describe)"
+HBM_BYTES_PER_INPUT_PIXEL = 321.0  # compulsory stage-boundary traffic, doubling on
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic data: generator "D"  -- sum of unit-variance Gaussian-filtered noise
+# fields at sigma 2,4,8,16,32 with wrap-around, mapped to [0,255] u8.  Built on the GPU with FFTs
+# (circular convolution == scipy's mode="wrap"); seed 1234 + image index.
+# ------------------------------------------------------------------------------------------
+def synth_image_gpu(h, w, seed, device):
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+
+    def response(n, s, half):
+        # scipy.ndimage.gaussian_filter's kernel: radius int(4 sigma + 0.5), normalised, wrapped
+        r = int(4.0 * s + 0.5)
+        x = torch.arange(-r, r + 1, device=device, dtype=torch.float64)
+        k = torch.exp(-0.5 * x * x / (s * s))
+        k = k / k.sum()
+        line = torch.zeros(n, device=device, dtype=torch.float64)
+        line.index_add_(0, (x.long() % n), k)
+        return (torch.fft.rfft(line) if half else torch.fft.fft(line)).real.float()
+
+    acc = torch.zeros((h, w), device=device)
+    for s in (2.0, 4.0, 8.0, 16.0, 32.0):
+        f = torch.fft.rfft2(torch.randn((h, w), generator=g, device=device, dtype=torch.float32))  # fresh field
+        n = torch.fft.irfft2(f * response(h, s, False).view(-1, 1) * response(w, s, True).view(1, -1), s=(h, w))
+        acc += n / n.std()
+    acc = (acc - acc.min()) / (acc.max() - acc.min()) * 255.0
+    return torch.round(acc).to(torch.uint8).contiguous()
+
+
+def pyramid_algorithmic_bytes(w, h, doubled=True):
+    """Compulsory HBM bytes of the Gaussian/DoG pyramid stage for one image:
+    per octave read the base (4 B/px), write G1..G3 (12), write D0..D4 (20), write the next base."""
+    bw, bh = (2 * w, 2 * h) if doubled else (w, h)
+    octaves = int(math.floor(math.log2(min(bw, bh) // 3)))
+    total = 0
+    for o in range(octaves):
+        p = bw * bh
+        total += 36 * p
+        bw, bh = bw // 2, bh // 2
+        if o + 1 < octaves:
+            total += 4 * bw * bh
+    return total
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.p is None:
+            return None
+        time.sleep(0.25)
+        self.p.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                if t0 - 0.1 <= t <= t1 + 0.3:
+                    sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own CPU implementation (oracle/_ref, the real
+# reference compiled from its sources; "port" = oracle/liboracle.so if that is absent)
+# ------------------------------------------------------------------------------------------
+def _cpu_worker_init():
+    global _W
+    from oracle import oracle as O
+    d = tempfile.mkdtemp(prefix="siftref_")
+    os.chdir(d)  # the reference's public entry point writes ./keypoints.png (sift.cpp:765-768)
+    _W = {"O": O, "kind": "reference" if O.have_ref() else "port"}
+    if _W["kind"] == "reference":
+        O.ref()
+    else:
+        O.port()
+
+
+def _cpu_detect(img):
+    O = _W["O"]
+    t = time.perf_counter()
+    if _W["kind"] == "reference":
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)  # silence the reference's per-stage std::cout chatter
+        try:
+            n = len(O.ref_detect_public(img))
+        finally:
+            os.dup2(saved, 1)
+            os.close(devnull); os.close(saved)
+    else:
+        n = len(O.Run(O.port(), img, keep_pyramid=False).keypoints(2))
+    return n, time.perf_counter() - t
+
+
+def cpu_kind():
+    from oracle import oracle as O
+    return "reference" if O.have_ref() else "port"
+
+
+def host_synth_crop(h, w, seed):
+    from oracle import oracle as O
+    return O.synth_image(h, w, seed=seed)
+
+
+def run_reference_arm(args):
+    """bench.py --impl reference: every host core runs the reference detect on its own
+    960x540 sample (1/16 of a 4K image's pixels, same generator); value is scaled by pixels."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    sh, sw = 540, 960
+    frac = (sh * sw) / (H4K * W4K)
+    imgs = [host_synth_crop(sh, sw, 1234 + i) for i in range(cores)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores, initializer=_cpu_worker_init) as pool:
+        times = []
+        for step in range(args.warmup + args.steps):
+            t = time.perf_counter()
+            res = pool.map(_cpu_detect, imgs, chunksize=1)
+            dt = time.perf_counter() - t
+            if step >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = args.steps * cores * frac / total
+    kind = cpu_kind()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic 3840x2160 (4K) batch of 256 images, detect+describe",
+                   "sample": f"{cores} x 960x540 generator-D images per step (1/16 of a 4K image each), scaled by pixel count",
+                   "keypoints_per_sample": float(np.mean([r[0] for r in res]))},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind,
+                         "sample": f"{cores} processes x one 960x540 image per step; reference "
+                                   f"{'copy-free build of /root/reference/src (bit-identical output)' if kind == 'reference' else 'CPU port oracle/sift_oracle.cpp'}"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline_sample(img_u8_host):
+    """rank 0, N=1: the reference detect on one 1920x1080 crop (1/4 of a 4K image), 1 thread."""
+    import multiprocessing as mp
+    crop = np.ascontiguousarray(img_u8_host[:1080, :1920])
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(1, initializer=_cpu_worker_init) as pool:
+        n, dt = pool.apply(_cpu_detect, (crop,))
+    kind = cpu_kind()
+    return {"value": 0.25 / dt, "unit": "images/s", "cores": 1, "kind": kind,
+            "sample": f"one 1920x1080 crop (1/4 of the pixels) of batch image 0, {n} keypoints, {dt:.1f} s, "
+                      f"scaled by pixel count; "
+                      f"{'reference sources compiled copy-free (oracle/_ref)' if kind == 'reference' else 'oracle port'}"}
+
+
+# ------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import sift_project_b200 as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    batch = args.images
+    W, H = args.width, args.height
+    mine = list(range(rank, batch, world))
+    d_imgs = [synth_image_gpu(H, W, 1234 + i, dev) for i in mine]
+    torch.cuda.synchronize()
+    n_ctx = args.contexts
+    ctxs = [S.SiftContext(W, H, device=local) for _ in range(n_ctx)]
+    streams = [torch.cuda.ExternalStream(c.stream, device=dev) for c in ctxs]
+    main = torch.cuda.current_stream()
+
+    # one verification pass: keypoint counts per image, no overflow
+    counts = []
+    for k, img in enumerate(d_imgs[: min(len(d_imgs), 4)]):
+        ctxs[0].detect_enqueue(img, W, H)
+        counts.append(ctxs[0].detect_finish())
+    kp_mean = float(np.mean(counts)) if counts else 0.0
+
+    def one_step_device():
+        for k, img in enumerate(d_imgs):
+            ctxs[k % n_ctx].detect_enqueue(img, W, H)
+
+    def join_streams():
+        for s in streams:
+            e = torch.cuda.Event()
+            e.record(s)
+            main.wait_event(e)
+
+    # ---- value: device-resident inputs and outputs ----
+    for _ in range(args.warmup):
+        one_step_device()
+    join_streams()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = sum(c.launches for c in ctxs)
+    t_wall0 = time.time()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record(main)
+    for s in streams:
+        s.wait_event(start)
+    for _ in range(args.steps):
+        one_step_device()
+    join_streams()
+    end.record(main)
+    barrier()
+    t_wall1 = time.time()
+    ms_dev = reduce_max(start.elapsed_time(end))
+    launches = reduce_sum(sum(c.launches for c in ctxs) - l0)
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    for c in ctxs:
+        c.detect_finish()
+    value = batch * args.steps / (ms_dev * 1e-3)
+
+    # ---- e2e: pinned host pixels in, host keypoint records out, through the C-ABI ----
+    h_imgs = [img.cpu().pin_memory() for img in d_imgs]
+    cap = int(max(counts) * 1.5) + 4096 if counts else 65536
+    outs = [np.zeros(cap, dtype=S.KP_DTYPE) for _ in range(n_ctx)]
+    for o in outs:
+        torch.cuda.cudart().cudaHostRegister(o.ctypes.data, o.nbytes, 0)
+
+    def one_step_e2e():
+        d2h = 0
+        pending = [False] * n_ctx
+        for k, img in enumerate(h_imgs):
+            j = k % n_ctx
+            if pending[j]:
+                d2h += ctxs[j].result_copy(outs[j]) * 168
+            ctxs[j].detect_enqueue(img, W, H)
+            pending[j] = True
+        for j in range(n_ctx):
+            if pending[j]:
+                d2h += ctxs[j].result_copy(outs[j]) * 168
+        return d2h
+
+    for _ in range(max(1, args.warmup // 2)):
+        one_step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    d2h_bytes = 0
+    for _ in range(args.steps):
+        d2h_bytes += one_step_e2e()
+    barrier()
+    e2e_s = reduce_max(time.perf_counter() - t0)
+    e2e_value = batch * args.steps / e2e_s
+    h2d_step = reduce_sum(len(h_imgs) * W * H)
+    d2h_step = reduce_sum(d2h_bytes / args.steps)
+
+    # ---- per-stage device times + roofline of the dominant (pyramid) kernel: one context, one
+    # stream, events around every stage, same images ----
+    roof = stages = stage_launches = None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    if rank == 0:
+        c0 = ctxs[0]
+        c0.set_profiling(True)
+        acc = None
+        reps = min(len(d_imgs), 16)
+        for k in range(reps + 2):
+            c0.detect_enqueue(d_imgs[k % len(d_imgs)], W, H)
+            ms, nl = c0.profile()
+            if k >= 2:
+                acc = ms if acc is None else {s: acc[s] + ms[s] for s in ms}
+        c0.set_profiling(False)
+        stages = {s: acc[s] / reps for s in acc}
+        stage_launches = nl
+        pyr_bytes = pyramid_algorithmic_bytes(W, H)
+        hbm_peak = peaks.get("hbm_gbs")
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (sustained copy)" if hbm_peak else "fallback 6650 GB/s (B200_PROFILING.md)"
+        hbm_peak = hbm_peak or 6650.0
+        achieved = pyr_bytes / (stages["pyramid"] * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("pyramid_dram_bytes_per_image")
+        except Exception:
+            pass
+        total_ms = sum(stages.values())
+        roof = {"bound": "hbm", "kernel": "pyramid (k_blur launches of one image)", "achieved": achieved,
+                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                "algorithmic_bytes": pyr_bytes, "ms": stages["pyramid"], "launches": nl["pyramid"],
+                "peak_source": peak_src,
+                "whole_detect": {"algorithmic_bytes": HBM_BYTES_PER_INPUT_PIXEL * W * H, "ms": total_ms,
+                                 "frac": HBM_BYTES_PER_INPUT_PIXEL * W * H / (total_ms * 1e-3) / 1e9 / hbm_peak}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline_sample(h_imgs[0].numpy())
+        except Exception as ex:  # the oracle is only a reported baseline; never fatal
+            cpu = {"error": repr(ex)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"synthetic {W}x{H} batch of {batch} images, detect+describe, sharded by image",
+                       "global_batch": batch, "images_per_rank": len(mine), "contexts_per_gpu": n_ctx,
+                       "generator": "D (sum of Gaussian-filtered noise, sigma 2..32), seed 1234+i",
+                       "keypoints_per_image": kp_mean, "octaves": ctxs[0].stats()["octaves"],
+                       "l2": "inputs larger than L2 (each image's pyramid is ~2 GB; 126 MB L2)",
+                       "parallelism": f"dp{world} by image, no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_step,
+                    "d2h_bytes_per_step": d2h_step, "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "stages_ms": stages, "stage_launches": stage_launches,
+        }
+        print(json.dumps(line))
+    for c in ctxs:
+        c.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--images", type=int, default=256, help="global batch (config: 256)")
+    ap.add_argument("--width", type=int, default=W4K)
+    ap.add_argument("--height", type=int, default=H4K)
+    ap.add_argument("--contexts", type=int, default=3, help="contexts (streams) in flight per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -96,12 +96,17 @@ int sift_b200_detect_f32(sift_b200_ctx* ctx, const float* pixels, int width, int
                          int channels, const sift_b200_params* params, sift_b200_keypoint* out,
                          int capacity, int* count);
 
-/* Device-resident variant: enqueue the whole pipeline on the context's stream and leave the
- * results on the GPU.  d_pixels must be DEVICE memory.  No host synchronisation happens. */
-int sift_b200_detect_enqueue_u8(sift_b200_ctx* ctx, const uint8_t* d_pixels, int width, int height,
+/* Asynchronous variant: enqueue the whole pipeline on the context's stream and leave the
+ * results on the GPU; no host synchronisation happens.  pixels may be DEVICE memory (used in
+ * place) or HOST memory (copied with cudaMemcpyAsync first -- pin it for a truly asynchronous
+ * copy; it must stay valid until the stream has consumed it). */
+int sift_b200_detect_enqueue_u8(sift_b200_ctx* ctx, const uint8_t* pixels, int width, int height,
                                 int channels, const sift_b200_params* params);
 /* Wait for the enqueued work; returns the number of final keypoints in *count. */
 int sift_b200_detect_finish(sift_b200_ctx* ctx, int* count);
+/* Wait, then copy the records of the last detect to a HOST array (same contract as
+ * sift_b200_detect_u8's out / capacity / count). */
+int sift_b200_result_copy(sift_b200_ctx* ctx, sift_b200_keypoint* out, int capacity, int* count);
 /* Device pointers to the results of the last detect: `n` 168-byte records and the dense
  * n x 128 u8 descriptor matrix (row i = record i's desc), valid until the next detect. */
 int sift_b200_result_device(sift_b200_ctx* ctx, const sift_b200_keypoint** d_records,
@@ -141,6 +146,21 @@ int sift_b200_debug_keypoints(sift_b200_ctx* ctx, int stage, sift_b200_keypoint*
                               int capacity, int* count);
 /* number of kernel launches issued by this context since creation (bench's gpu_launches) */
 long sift_b200_launch_count(const sift_b200_ctx* ctx);
+
+/* ---- per-stage device timing (CUDA events on the context's stream) ---- */
+#define SIFT_B200_STAGE_INPUT 0    /* gray + 2x upsample + initial blur (sift.cpp:113-126) */
+#define SIFT_B200_STAGE_PYRAMID 1  /* Gaussian cascade + DoG + decimation (sift.cpp:181-225) */
+#define SIFT_B200_STAGE_EXTREMA 2  /* sift.cpp:264-319 */
+#define SIFT_B200_STAGE_REFINE 3   /* sift.cpp:330-436 */
+#define SIFT_B200_STAGE_ORIENT 4   /* sift.cpp:447-533 */
+#define SIFT_B200_STAGE_SORT 5     /* sift.cpp:20-24 */
+#define SIFT_B200_STAGE_DESCRIBE 6 /* sift.cpp:610-682 */
+#define SIFT_B200_STAGE_COUNT 7
+/* When on, every detect call brackets its stages with events (a few microseconds each). */
+int sift_b200_set_profiling(sift_b200_ctx* ctx, int on);
+/* Milliseconds and kernel-launch counts per stage of the last profiled detect (arrays of
+ * SIFT_B200_STAGE_COUNT); waits for the stream. */
+int sift_b200_get_profile(sift_b200_ctx* ctx, float* stage_ms, int32_t* stage_launches);
 
 #ifdef __cplusplus
 }

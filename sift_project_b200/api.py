@@ -96,6 +96,9 @@ def load_library():
         "sift_b200_debug_extrema": (i32, [vp, vp, i32, i32p]),
         "sift_b200_debug_keypoints": (i32, [vp, i32, vp, i32, i32p]),
         "sift_b200_launch_count": (C.c_long, [vp]),
+        "sift_b200_result_copy": (i32, [vp, vp, i32, i32p]),
+        "sift_b200_set_profiling": (i32, [vp, i32]),
+        "sift_b200_get_profile": (i32, [vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -184,10 +187,28 @@ class SiftContext:
             self._check(rc)
             return out[: n.value].copy()
 
-    def detect_enqueue(self, d_image_u8, width, height, channels=1, **params):
+    def detect_enqueue(self, image_u8, width, height, channels=1, **params):
+        """image_u8: torch CUDA tensor, (pinned) host array / tensor, or a raw pointer."""
         p = make_params(**params)
-        self._check(self._L.sift_b200_detect_enqueue_u8(self._h, _ptr(d_image_u8), width, height, channels,
+        self._check(self._L.sift_b200_detect_enqueue_u8(self._h, _ptr(image_u8), width, height, channels,
                                                         C.byref(p)))
+
+    def result_copy(self, out):
+        """Wait and copy the last detect's records into `out` (numpy KP_DTYPE array); returns count."""
+        n = C.c_int(0)
+        self._check(self._L.sift_b200_result_copy(self._h, out.ctypes.data, len(out), C.byref(n)))
+        return n.value
+
+    STAGES = ("input", "pyramid", "extrema", "refine", "orient", "sort", "describe")
+
+    def set_profiling(self, on):
+        self._check(self._L.sift_b200_set_profiling(self._h, int(on)))
+
+    def profile(self):
+        ms = np.zeros(len(self.STAGES), np.float32)
+        nl = np.zeros(len(self.STAGES), np.int32)
+        self._check(self._L.sift_b200_get_profile(self._h, ms.ctypes.data, nl.ctypes.data))
+        return dict(zip(self.STAGES, ms.tolist())), dict(zip(self.STAGES, nl.tolist()))
 
     def detect_finish(self):
         n = C.c_int(0)

@@ -54,6 +54,11 @@ struct sift_b200_ctx {
     bool have_result = false;
     int base_w = 0, base_h = 0;
     sift_b200_stats stats{};
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_stage;   // stage of the interval ending at event i (event 0: -1)
+    int ev_used = 0;
+    int stage_launches[SIFT_B200_STAGE_COUNT] = {0};
 
     // ---- match workspace (grown on demand) ----
     MatchScratch ms{};
@@ -198,6 +203,22 @@ int enqueue_match(sift_b200_ctx* c, const uint8_t* d_a, int na, const uint8_t* d
     return SIFT_B200_OK;
 }
 
+// Profiling: mark(stage) closes an interval [previous event, now) attributed to `stage`.
+void prof_mark(sift_b200_ctx* c, int stage, int launches = 0) {
+    if (stage >= 0) c->stage_launches[stage] += launches;
+    c->launches += launches;
+    if (!c->profiling) return;
+    if (c->ev_used == (int)c->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        c->ev_pool.push_back(e);
+        c->ev_stage.push_back(-1);
+    }
+    cudaEventRecord(c->ev_pool[c->ev_used], c->stream);
+    c->ev_stage[c->ev_used] = stage;
+    c->ev_used++;
+}
+
 template <typename T>
 int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, int channels,
                    const sift_b200_params& p) {
@@ -242,6 +263,9 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     c->stats.base_width = bw;
     c->stats.base_height = bh;
     c->have_result = false;
+    c->ev_used = 0;
+    memset(c->stage_launches, 0, sizeof c->stage_launches);
+    prof_mark(c, -1);
     if (octaves == 0) {
         c->detect_pending = true;
         CU(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
@@ -270,7 +294,7 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
         CU(c, launch_prepare_f32((const float*)d_pixels, width, height, channels, scratch, bw, bh, o0.pitch,
                                  doubled, s));
     CU(c, launch_blur(scratch, o0.G[0], nullptr, nullptr, bw, bh, o0.pitch, 0, 0, 0, taps[0], s));
-    c->launches += 2;
+    prof_mark(c, SIFT_B200_STAGE_INPUT, 2);
 
     for (int o = 0; o < octaves; ++o) {
         OctaveDesc& od = c->pyr.oct[o];
@@ -282,23 +306,24 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
                 dec = nx.G[0]; dw = nx.w; dh = nx.h; dp = nx.pitch;
             }
             CU(c, launch_blur(od.G[i - 1], od.G[i], od.D[i - 1], dec, od.w, od.h, od.pitch, dw, dh, dp, taps[i], s));
-            c->launches += 1;
         }
+        prof_mark(c, SIFT_B200_STAGE_PYRAMID, kLayers - 1);
         if (od.w >= 3 && od.h >= 3) {
             CU(c, launch_extrema(od, o, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, s));
-            c->launches += 1;
+            prof_mark(c, SIFT_B200_STAGE_EXTREMA, 1);
         }
     }
     CU(c, launch_refine(c->d_pyr, c->d_cands, c->d_raw, c->d_counters, sp, s));
+    prof_mark(c, SIFT_B200_STAGE_REFINE, 1);
     CU(c, launch_orient(c->d_pyr, c->d_raw, c->d_oriented, c->d_counters, sp, s));
-    c->launches += 2;
+    prof_mark(c, SIFT_B200_STAGE_ORIENT, 1);
     c->ss.nb = std::min(width + 2, c->ss_nb_cap);
     int l = 0;
     CU(c, launch_sort_dedup(c->d_oriented, c->d_counters, c->ss, sp, s, &l));
-    c->launches += l;
+    prof_mark(c, SIFT_B200_STAGE_SORT, l);
     CU(c, launch_describe(c->d_pyr, c->d_oriented, c->ss.final_order, c->d_counters, c->d_records, c->d_desc,
                           c->cap_oriented, sp, s));
-    c->launches += 1;
+    prof_mark(c, SIFT_B200_STAGE_DESCRIBE, 1);
     CU(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
     c->detect_pending = true;
     return SIFT_B200_OK;
@@ -462,6 +487,7 @@ void sift_b200_destroy(sift_b200_ctx* c) {
                     c->d_out_ia, c->d_out_ib, c->d_out_dist, c->d_out_count};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
@@ -478,14 +504,66 @@ int sift_b200_detect_f32(sift_b200_ctx* c, const float* pixels, int width, int h
     return detect_sync<float>(c, pixels, width, height, channels, params, out, capacity, count);
 }
 
-int sift_b200_detect_enqueue_u8(sift_b200_ctx* c, const uint8_t* d_pixels, int width, int height, int channels,
+int sift_b200_detect_enqueue_u8(sift_b200_ctx* c, const uint8_t* pixels, int width, int height, int channels,
                                 const sift_b200_params* params) {
     if (!c) return SIFT_B200_E_INVALID;
-    if (!d_pixels) return fail(c, SIFT_B200_E_INVALID, "null argument");
+    if (!pixels) return fail(c, SIFT_B200_E_INVALID, "null argument");
+    if (width < 2 || height < 2) return fail(c, SIFT_B200_E_INVALID, "image %dx%d is too small", width, height);
+    if (channels != 1 && channels != 3) return fail(c, SIFT_B200_E_INVALID, "channels must be 1 or 3");
     CU(c, cudaSetDevice(c->device));
     sift_b200_params p;
     if (params) p = *params; else sift_b200_default_params(&p);
-    return enqueue_detect<uint8_t>(c, d_pixels, width, height, channels, p);
+    const uint8_t* d_px = pixels;
+    if (!is_device_ptr(pixels)) {
+        const size_t bytes = (size_t)width * height * channels;
+        if (bytes > c->input_bytes)
+            return fail(c, SIFT_B200_E_TOO_LARGE, "image %dx%dx%d exceeds the context's staging buffer", width,
+                        height, channels);
+        CU(c, cudaMemcpyAsync(c->d_input, pixels, bytes, cudaMemcpyHostToDevice, c->stream));
+        d_px = c->d_input;
+    }
+    return enqueue_detect<uint8_t>(c, d_px, width, height, channels, p);
+}
+
+int sift_b200_result_copy(sift_b200_ctx* c, sift_b200_keypoint* out, int capacity, int* count) {
+    if (!c || !count || (capacity > 0 && !out)) return SIFT_B200_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    int n = 0;
+    int rc = finish_detect(c, &n);
+    *count = n;
+    if (rc) return rc;
+    const int ncopy = std::min(n, capacity);
+    if (ncopy > 0) {
+        CU(c, cudaMemcpyAsync(out, c->d_records, (size_t)ncopy * sizeof(sift_b200_keypoint),
+                              cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    if (n > capacity) return fail(c, SIFT_B200_E_CAPACITY, "%d keypoints found, output capacity %d", n, capacity);
+    return SIFT_B200_OK;
+}
+
+int sift_b200_set_profiling(sift_b200_ctx* c, int on) {
+    if (!c) return SIFT_B200_E_INVALID;
+    c->profiling = on != 0;
+    c->ev_used = 0;
+    return SIFT_B200_OK;
+}
+
+int sift_b200_get_profile(sift_b200_ctx* c, float* stage_ms, int32_t* stage_launches) {
+    if (!c || !stage_ms) return SIFT_B200_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < SIFT_B200_STAGE_COUNT; ++i) {
+        stage_ms[i] = 0.f;
+        if (stage_launches) stage_launches[i] = c->stage_launches[i];
+    }
+    for (int i = 1; i < c->ev_used; ++i) {
+        float ms = 0.f;
+        CU(c, cudaEventElapsedTime(&ms, c->ev_pool[i - 1], c->ev_pool[i]));
+        const int st = c->ev_stage[i];
+        if (st >= 0 && st < SIFT_B200_STAGE_COUNT) stage_ms[st] += ms;
+    }
+    return SIFT_B200_OK;
 }
 
 int sift_b200_detect_finish(sift_b200_ctx* c, int* count) {

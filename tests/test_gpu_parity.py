@@ -221,7 +221,7 @@ def test_small_and_odd_sizes(ctx):
     for h, w in ((2, 2), (3, 5), (7, 9), (17, 33), (64, 31), (129, 257)):
         img = O.synth_image(max(h, 8), max(w, 8), seed=h * w)[:h, :w]
         got = ctx.detect(img)
-        run = O.Run(O.port(), img, keep_pyramid=False)
+        run = O.Run(O.port(), img, keep_pyramid=True)
         want = run.keypoints(2)
         assert ctx.stats()["octaves"] == run.octaves, (h, w)
         rec, prec, _, _ = P.recall_precision(got, want)
