@@ -179,16 +179,22 @@ k_refine(const PyramidDesc* __restrict__ pyr, const Cand* __restrict__ cands, Kp
 
 // ------------------------------------------------------------------------------------------
 // Orientation -- sift.cpp:447-533.  One warp per raw keypoint; lanes stride over the
-// (2r+1)^2 window; 36-bin histogram in shared memory (fixed point); lane 0 smooths in place
-// (sequentially, exactly like the reference) and emits one keypoint per qualifying peak.
+// (2r+1)^2 window; 36-bin histogram in shared memory, privatised 8x to thin out bank conflicts,
+// accumulated as 32-bit fixed point (integer adds commute => bit-reproducible); lane 0 smooths in
+// place (sequentially, exactly like the reference) and emits one keypoint per qualifying peak.
+// Fixed-point scale: a bin can receive at most sum(w) * max|grad| <= (1 + sqrt(2 pi) s)^2 * 361
+// for pixel values in [0, 255], which is mapped to 2^32.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int ORI_COPIES = 8;
+
+__global__ void __launch_bounds__(256, 2)
 k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, KpCore* __restrict__ oriented,
          Counters* __restrict__ counters, const StageParams sp) {
-    __shared__ unsigned long long s_hist[8][kOriBins];
+    __shared__ unsigned s_hist[8][ORI_COPIES][kOriBins];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = min(counters->n_raw, sp.cap_raw);
-    unsigned long long* hist = s_hist[warp];
+    unsigned* hist = &s_hist[warp][0][0];
+    unsigned* my_hist = s_hist[warp][lane & (ORI_COPIES - 1)];
     for (int i = blockIdx.x * 8 + warp; i < n; i += gridDim.x * 8) {
         const KpCore kp = raw[i];
         const OctaveDesc& oc = pyr->oct[kp.octave];
@@ -199,17 +205,22 @@ k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, Kp
         const double scale = sp.ori_sigma_factor * (kp.size * inv);
         const int radius = (int)round(3.0 * scale);
         const float neg_inv_denom = (float)(-1.0 / (2.0 * scale * scale));
-        for (int b = lane; b < kOriBins; b += 32) hist[b] = 0ull;
+        const double g1 = 1.0 + 2.5066282746310002 * scale;
+        const double bound = g1 * g1 * 361.0;
+        const float fix = (float)(4294967296.0 / bound);
+        const double unfix = bound / 4294967296.0;
+        for (int b = lane; b < ORI_COPIES * kOriBins; b += 32) hist[b] = 0u;
         __syncwarp();
-        const int side = 2 * radius + 1;
-        const int total = side * side;
+        // window clipped to the pixels whose 4-neighbourhood is inside the image (sift.cpp:473,478)
+        const int i_lo = max(-radius, 1 - x), i_hi = min(radius, W - 2 - x);
+        const int j_lo = max(-radius, 1 - y), j_hi = min(radius, H - 2 - y);
+        const int side = i_hi - i_lo + 1;
+        const int total = (side > 0 && j_hi >= j_lo) ? side * (j_hi - j_lo + 1) : 0;
         for (int s = lane; s < total; s += 32) {
-            const int jr = s / side;             // row of the window -> y offset
-            const int i_off = s - jr * side - radius;
-            const int j_off = jr - radius;
-            const int px = x + i_off, py = y + j_off;
-            if (px - 1 < 0 || px + 1 >= W || py - 1 < 0 || py + 1 >= H) continue;
-            const float* c = img + (size_t)py * pitch + px;
+            const int jr = s / side;
+            const int i_off = i_lo + (s - jr * side);
+            const int j_off = j_lo + jr;
+            const float* c = img + (size_t)(y + j_off) * pitch + (x + i_off);
             const float dx = ldg(c + 1) - ldg(c - 1);
             const float dy = ldg(c - pitch) - ldg(c + pitch);  // up minus down, sift.cpp:483
             const float mag = sqrtf(dx * dx + dy * dy);
@@ -218,13 +229,17 @@ k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, Kp
             int b = (int)roundf((float)kOriBins * (ang + 3.14159265358979323846f) * (1.0f / 6.283185307179586f));
             b = (b < kOriBins) ? b : 0;  // sift.cpp:489-490: bin 0 <-> angle -pi
             b = max(b, 0);
-            const long long fx = __float2ll_rn(wgt * mag * kFix);
-            atomicAdd(&hist[b], (unsigned long long)fx);
+            atomicAdd(&my_hist[b], __float2uint_rn(wgt * mag * fix));
         }
         __syncwarp();
         if (lane == 0) {
             double hd[kOriBins];
-            for (int b = 0; b < kOriBins; ++b) hd[b] = (double)(long long)hist[b] * kUnfix;
+            for (int b = 0; b < kOriBins; ++b) {
+                unsigned long long t = 0;
+#pragma unroll
+                for (int cpy = 0; cpy < ORI_COPIES; ++cpy) t += hist[cpy * kOriBins + b];
+                hd[b] = (double)t * unfix;
+            }
             for (int it = 0; it < 2; ++it)  // ORI_SMOOTH_ITERATIONS; in place, sequential
                 for (int b = 0; b < kOriBins; ++b)
                     hd[b] = 0.25 * hd[(b - 1 + kOriBins) % kOriBins] + 0.5 * hd[b] +
@@ -383,17 +398,29 @@ __global__ void __launch_bounds__(256) k_bucket_gather(SortScratch ss) {
 
 // ------------------------------------------------------------------------------------------
 // Descriptors -- sift.cpp:610-682 (compute_descriptors), :541-571 (update_histogram, trilinear),
-// :576-603 (convert_hist_to_desc).  One warp per final keypoint, lanes stride over the rotated
-// (2r+1)^2 window, 4x4x8 fixed-point histogram in shared memory, FP64 normalise / clamp 0.2 /
-// renormalise / floor(512 x) / min 255.  Writes the 168-byte record and the dense 128-byte row.
+// :576-603 (convert_hist_to_desc).  One warp per final keypoint.  The reference walks the whole
+// (2r+1)^2 window and rejects about half of it; here each lane first bounds, per window row, the
+// column interval that can pass the rotated-bin test (a conservative superset, the exact test is
+// still evaluated per sample), the intervals are flattened with a warp scan and the 32 lanes
+// stride over the flattened list, so nearly every lane-iteration is a contributing sample.
+// 4x4x8 histogram in shared memory as 32-bit fixed point (integer adds commute =>
+// bit-reproducible), two copies per warp (odd / even lanes) to thin out conflicts.  Scale: one bin
+// receives at most sum(tent_r * tent_c) * max|grad| <= (hw + 2)^2 * 361 for pixel values in
+// [0, 255]; the descriptor is normalised afterwards, so the scale cancels.
+// FP64 normalise / clamp 0.2 / renormalise / floor(512 x) / min 255.  Writes the 168-byte record
+// and the dense 128-byte row.
 // ------------------------------------------------------------------------------------------
+constexpr int DESC_COPIES = 2;
+
 __global__ void __launch_bounds__(256)
 k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ oriented,
            const int* __restrict__ final_order, const Counters* __restrict__ counters,
            uint8_t* __restrict__ records, uint8_t* __restrict__ desc, int cap_final, const StageParams sp) {
-    __shared__ unsigned long long s_hist[8][128];
+    __shared__ unsigned s_hist[8][DESC_COPIES][128];
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long* hist = s_hist[warp];
+    unsigned* hist = &s_hist[warp][0][0];
+    unsigned* my_hist = s_hist[warp][lane & (DESC_COPIES - 1)];
     const int n = min(counters->n_final, cap_final);
     for (int i = blockIdx.x * 8 + warp; i < n; i += gridDim.x * 8) {
         const KpCore kp = oriented[final_order[i]];
@@ -410,49 +437,88 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
         const float ca = (float)cos(kp.pori), sa = (float)sin(kp.pori);
         const float inv_hw = (float)(1.0 / hw);
         const float pori = (float)kp.pori;
-        for (int b = lane; b < 128; b += 32) hist[b] = 0ull;
+        const float fix = (float)(4294967296.0 / ((hw + 2.0) * (hw + 2.0) * 361.0));
+        for (int b = lane; b < DESC_COPIES * 128; b += 32) hist[b] = 0u;
         __syncwarp();
-        const int side = 2 * radius + 1;
-        const int total = side * side;
-        for (int s = lane; s < total; s += 32) {
-            const int rr_i = s / side;
-            const int col = s - rr_i * side - radius;
-            const int row = rr_i - radius;
-            const float rr = ((float)col * sa + (float)row * ca) * inv_hw;
-            const float cr = ((float)col * ca - (float)row * sa) * inv_hw;
-            const float rb = rr + 1.5f, cb = cr + 1.5f;  // + DESC_HIST_WIDTH/2 - 0.5 (integer 4/2)
-            if (!(rb > -1.0f && rb < 4.0f && cb > -1.0f && cb < 4.0f)) continue;
-            const int ny = row + y, nx = col + x;
-            if (!(nx > 0 && nx < W - 1 && ny > 0 && ny < H - 1)) continue;
-            const float* c = img + (size_t)ny * pitch + nx;
-            const float dx = ldg(c + 1) - ldg(c - 1);
-            const float dy = ldg(c - pitch) - ldg(c + pitch);
-            const float mag = sqrtf(dx * dx + dy * dy);
-            float ang = atan2f(dy, dx) - pori;  // in (-3pi, pi]
-            ang -= 6.283185307179586f * floorf(ang * (1.0f / 6.283185307179586f));
-            if (ang < 0.f) ang = 0.f;
-            if (ang >= 6.283185307179586f) ang -= 6.283185307179586f;
-            const float ob = ang * (8.0f / 6.283185307179586f);
-            const float wgt = __expf(-(rr * rr + cr * cr) * 0.125f);
-            const float m = mag * wgt;
-            const float fbr = floorf(rb), fbc = floorf(cb), fbo = floorf(ob);
-            const int br = (int)fbr, bc = (int)fbc, bo = (int)fbo;
-            const float fr = rb - fbr, fc = cb - fbc, fo = ob - fbo;
+        // |col*sa + row*ca| < 2.5 hw  and  |col*ca - row*sa| < 2.5 hw  (bins in (-1, 4)), widened
+        const float lim = 2.5f * (float)hw + 0.5f;
+        for (int row0 = -radius; row0 <= radius; row0 += 32) {
+            const int row = row0 + lane;
+            int lo = -radius, hi = radius;
+            const int ny = row + y;
+            if (row > radius || !(ny > 0 && ny < H - 1)) hi = lo - 1;
+            lo = max(lo, 1 - x);
+            hi = min(hi, W - 2 - x);
+            {
+                const float b1 = (float)row * ca, b2 = -(float)row * sa;
+                // strip a*col + b in (-lim, lim)
+                auto clip = [&](float a, float b) {
+                    if (fabsf(a) < 1e-6f) {
+                        if (!(fabsf(b) < lim + 1.0f)) hi = lo - 1;
+                        return;
+                    }
+                    const float t0 = (-lim - b) / a, t1 = (lim - b) / a;
+                    const float mn = fminf(t0, t1), mx = fmaxf(t0, t1);
+                    if (mn > (float)lo) lo = max(lo, (int)floorf(mn));
+                    if (mx < (float)hi) hi = min(hi, (int)ceilf(mx));
+                };
+                clip(sa, b1);
+                clip(ca, b2);
+            }
+            const int cnt = max(0, hi - lo + 1);
+            int off = cnt;  // inclusive scan
 #pragma unroll
-            for (int a = 0; a <= 1; ++a) {
-                const int ri = br + a;
-                if (ri < 0 || ri >= 4) continue;
-                const float vr = m * (a == 0 ? 1.0f - fr : fr);
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(FULL, off, d);
+                if (lane >= d) off += t;
+            }
+            const int total = __shfl_sync(FULL, off, 31);
+            off -= cnt;  // exclusive
+            for (int s0 = 0; s0 < total; s0 += 32) {
+                const int s = s0 + lane;
+                // row slot k = the last lane whose exclusive offset is <= s
+                int k = 0;
 #pragma unroll
-                for (int bq = 0; bq <= 1; ++bq) {
-                    const int ci = bc + bq;
-                    if (ci < 0 || ci >= 4) continue;
-                    const float vc = vr * (bq == 0 ? 1.0f - fc : fc);
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int o = __shfl_sync(FULL, off, k + step);
+                    if (o <= s) k += step;
+                }
+                const int off_k = __shfl_sync(FULL, off, k);
+                const int lo_k = __shfl_sync(FULL, lo, k);
+                if (s >= total) continue;
+                const int col = lo_k + (s - off_k);
+                const int rw = row0 + k;
+                const float rr = ((float)col * sa + (float)rw * ca) * inv_hw;
+                const float cr = ((float)col * ca - (float)rw * sa) * inv_hw;
+                const float rb = rr + 1.5f, cb = cr + 1.5f;  // + DESC_HIST_WIDTH/2 - 0.5 (integer 4/2)
+                if (!(rb > -1.0f && rb < 4.0f && cb > -1.0f && cb < 4.0f)) continue;
+                const float* c = img + (size_t)(rw + y) * pitch + (col + x);
+                const float dx = ldg(c + 1) - ldg(c - 1);
+                const float dy = ldg(c - pitch) - ldg(c + pitch);
+                const float mag = sqrtf(dx * dx + dy * dy);
+                float ang = atan2f(dy, dx) - pori;  // in (-3pi, pi]
+                ang -= 6.283185307179586f * floorf(ang * (1.0f / 6.283185307179586f));
+                if (ang < 0.f) ang = 0.f;
+                if (ang >= 6.283185307179586f) ang -= 6.283185307179586f;
+                const float ob = ang * (8.0f / 6.283185307179586f);
+                const float wgt = __expf(-(rr * rr + cr * cr) * 0.125f);
+                const float m = mag * wgt * fix;
+                const float fbr = floorf(rb), fbc = floorf(cb), fbo = floorf(ob);
+                const int br = (int)fbr, bc = (int)fbc, bo = (int)fbo;
+                const float fr = rb - fbr, fc = cb - fbc, fo = ob - fbo;
 #pragma unroll
-                    for (int d = 0; d <= 1; ++d) {
-                        const int oi = (bo + d) & 7;
-                        const float vo = vc * (d == 0 ? 1.0f - fo : fo);
-                        atomicAdd(&hist[(ri * 4 + ci) * 8 + oi], (unsigned long long)__float2ll_rn(vo * kFix));
+                for (int a = 0; a <= 1; ++a) {
+                    const int ri = br + a;
+                    if (ri < 0 || ri >= 4) continue;
+                    const float vr = m * (a == 0 ? 1.0f - fr : fr);
+#pragma unroll
+                    for (int bq = 0; bq <= 1; ++bq) {
+                        const int ci = bc + bq;
+                        if (ci < 0 || ci >= 4) continue;
+                        const float vc = vr * (bq == 0 ? 1.0f - fc : fc);
+                        unsigned* cell = my_hist + (ri * 4 + ci) * 8;
+                        atomicAdd(cell + (bo & 7), __float2uint_rn(vc * (1.0f - fo)));
+                        atomicAdd(cell + ((bo + 1) & 7), __float2uint_rn(vc * fo));
                     }
                 }
             }
@@ -463,11 +529,14 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
         double ss = 0.0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            hv[k] = (double)(long long)hist[4 * lane + k] * kUnfix;
+            unsigned long long t = 0;
+#pragma unroll
+            for (int cpy = 0; cpy < DESC_COPIES; ++cpy) t += hist[cpy * 128 + 4 * lane + k];
+            hv[k] = (double)t;
             ss += hv[k] * hv[k];
         }
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+        for (int d = 16; d >= 1; d >>= 1) ss += __shfl_xor_sync(FULL, ss, d);
         double inv_n = 1.0 / sqrt(ss);
         ss = 0.0;
 #pragma unroll
@@ -477,7 +546,7 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
             ss += hv[k] * hv[k];
         }
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+        for (int d = 16; d >= 1; d >>= 1) ss += __shfl_xor_sync(FULL, ss, d);
         inv_n = 1.0 / sqrt(ss);
         uint32_t packed = 0;
 #pragma unroll
