@@ -52,6 +52,13 @@ cudaError_t launch_norms(const uint8_t* d, int n, int* norms, cudaStream_t s);
 cudaError_t launch_match_simt(const uint8_t* a, int na, const uint8_t* b, int nb, int* best_idx,
                               int* best_d2, int* second_d2, const MatchScratch& ms, int sm_count,
                               cudaStream_t s, int* launches);
+cudaError_t launch_match_merge(const MatchScratch& ms, int splits, int na, int* best_idx, int* best_d2,
+                               int* second_d2, cudaStream_t s);
+// match_tc.cu: tcgen05 / TMA / TMEM path
+cudaError_t match_tc_init();
+int match_tc_padded_rows(int nb);
+cudaError_t launch_match_tc(const uint8_t* a, int na, const uint8_t* b, int nb, int* best_idx, int* best_d2,
+                            int* second_d2, const MatchScratch& ms, int sm_count, cudaStream_t s, int* launches);
 // match.cu: picks the tcgen05 kernel (match_tc.cu) for large problems, else the SIMT kernel
 cudaError_t match_init();
 bool match_uses_tensor_cores(int na, int nb);

@@ -181,6 +181,13 @@ cudaError_t launch_match_simt(const uint8_t* a, int na, const uint8_t* b, int nb
     return cudaGetLastError();
 }
 
+cudaError_t launch_match_merge(const MatchScratch& ms, int splits, int na, int* best_idx, int* best_d2,
+                               int* second_d2, cudaStream_t s) {
+    k_match_merge<<<(na + 255) / 256, 256, 0, s>>>(ms.part_idx, ms.part_d1, ms.part_d2, splits, na, best_idx,
+                                                  best_d2, second_d2);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_match_emit(const int* best_idx, const int* best_d2, const int* second_d2, int na, int nb,
                               double ratio, int* out_ia, int* out_ib, double* out_dist, int cap,
                               int* out_count, cudaStream_t s) {

@@ -259,3 +259,82 @@ def test_device_resident_enqueue_path(ctx, synth):
     assert n == len(host)
     rec, desc, n2 = ctx.result_device()
     assert n2 == n and rec and desc
+
+
+@pytest.fixture
+def force_path():
+    def _set(p):
+        if p is None:
+            os.environ.pop("SIFT_B200_MATCH", None)
+        else:
+            os.environ["SIFT_B200_MATCH"] = p
+    yield _set
+    os.environ.pop("SIFT_B200_MATCH", None)
+
+
+def _numpy_top2(a, b):
+    D = ((a.astype(np.int64)[:, None, :] - b.astype(np.int64)[None, :, :]) ** 2).sum(-1)
+    order = np.argsort(D, axis=1, kind="stable")
+    r = np.arange(len(a))
+    second = D[r, order[:, 1]] if b.shape[0] > 1 else np.full(len(a), 2 ** 31 - 1)
+    return order[:, 0], D[r, order[:, 0]], second
+
+
+@pytest.mark.parametrize("na,nb", [(1, 1), (5, 2), (128, 256), (129, 257), (300, 255), (1000, 1500), (2500, 3100)])
+@pytest.mark.parametrize("path", ["tc", "simt"])
+def test_match_paths_top2_exact(ctx, force_path, path, na, nb):
+    """Both matcher kernels (tcgen05 kind::i8 and SIMT dp4a) return the exact integer
+    (nearest index, d1^2, d2^2) of sift.cpp:789-806, including ties (lowest j) and duplicates."""
+    import torch
+    force_path(path)
+    assert ctx.match_path(na, nb) == (1 if path == "tc" else 0)
+    a, b = O.synth_descriptors(na, seed=na + 1), O.synth_descriptors(nb, seed=nb + 2)
+    if nb > 40:
+        b[nb - 1] = b[3]            # duplicate rows far apart (different tiles / splits)
+        b[nb // 2] = a[na // 2]     # exact hit
+        b[7] = a[0]; b[nb - 2] = a[0]   # two exact hits: best = lowest j, second distance 0
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    idx = torch.full((na,), -7, dtype=torch.int32, device="cuda")
+    d1, d2 = torch.zeros_like(idx), torch.zeros_like(idx)
+    torch.cuda.synchronize()
+    ctx.match_enqueue(ta, na, tb, nb, idx, d1, d2)
+    ctx.sync()
+    wi, w1, w2 = _numpy_top2(a, b)
+    assert np.array_equal(idx.cpu().numpy(), wi)
+    assert np.array_equal(d1.cpu().numpy(), w1)
+    assert np.array_equal(d2.cpu().numpy(), w2)
+
+
+def test_match_tc_extreme_values(ctx, force_path):
+    """All-255 against all-0 rows: the largest possible distance (128 * 255^2) and dot product."""
+    import torch
+    force_path("tc")
+    a = np.zeros((256, 128), np.uint8); a[::2] = 255
+    b = np.zeros((512, 128), np.uint8); b[1::2] = 255; b[5, :64] = 255
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    idx = torch.empty(256, dtype=torch.int32, device="cuda")
+    d1, d2 = torch.empty_like(idx), torch.empty_like(idx)
+    torch.cuda.synchronize()
+    ctx.match_enqueue(ta, 256, tb, 512, idx, d1, d2)
+    ctx.sync()
+    wi, w1, w2 = _numpy_top2(a, b)
+    assert np.array_equal(idx.cpu().numpy(), wi)
+    assert np.array_equal(d1.cpu().numpy(), w1) and np.array_equal(d2.cpu().numpy(), w2)
+
+
+def test_match_large_tc_vs_simt(ctx, force_path):
+    """20k x 20k (one pair of config 5): the two kernels agree bit for bit."""
+    import torch
+    a, b = O.synth_descriptors(20000, seed=11), O.synth_descriptors(20000, seed=12)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    out = {}
+    for path in ("tc", "simt"):
+        force_path(path)
+        idx = torch.empty(20000, dtype=torch.int32, device="cuda")
+        d1, d2 = torch.empty_like(idx), torch.empty_like(idx)
+        torch.cuda.synchronize()
+        ctx.match_enqueue(ta, 20000, tb, 20000, idx, d1, d2)
+        ctx.sync()
+        out[path] = (idx.cpu().numpy(), d1.cpu().numpy(), d2.cpu().numpy())
+    for x, y in zip(out["tc"], out["simt"]):
+        assert np.array_equal(x, y)
