@@ -186,8 +186,8 @@ int ensure_match_scratch(sift_b200_ctx* c, int na, int nb) {
     }
     if ((size_t)nb > c->ms_rows_b) {
         const size_t rows = std::max<size_t>((size_t)nb, 1024) * 5 / 4;
-        int rc;
-        if ((rc = grow_i32(c, &c->ms.norms_b, rows))) return rc;
+        int rc;  // + room for the tile padding and the per-tile minima of the tensor-core path
+        if ((rc = grow_i32(c, &c->ms.norms_b, rows + 1024 + rows / 64))) return rc;
         c->ms_rows_b = rows;
     }
     return SIFT_B200_OK;

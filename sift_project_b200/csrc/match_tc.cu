@@ -39,15 +39,16 @@ constexpr int KB = 128;            // descriptor bytes = K
 constexpr int STAGES = 4;          // B ring depth
 constexpr int A_BYTES = BM * KB;   // 16 KB
 constexpr int B_BYTES = BN * KB;   // 32 KB
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;          // 4 per scheduler: TMEM-lane quarter x 64-column slice
+constexpr int SLICE = BN / (EPI_WARPS / 4);  // columns per epilogue warp
 constexpr int NTHREADS = 32 * (2 + EPI_WARPS);
 constexpr int PAD_NORM = (1 << 23) - 1;  // > 128 * 255^2: padded columns never beat a real one
 
 struct __align__(1024) SmemLayout {
     uint8_t a[2][A_BYTES];
     uint8_t b[STAGES][B_BYTES];
-    int cprime[EPI_WARPS][BN / 2];   // per-warp staging of the per-column constants
-    int merge[BM][4];                // column-half 1 -> column-half 0 hand-over
+    int cprime[EPI_WARPS][SLICE];    // per-warp staging of the per-column constants
+    int merge[EPI_WARPS / 4][BM][4]; // column slices 1.. -> slice 0 hand-over
     unsigned long long full_b[STAGES], empty_b[STAGES];
     unsigned long long a_full[2], a_empty[2];
     unsigned long long tmem_full[2], tmem_empty[2];
@@ -115,26 +116,31 @@ __device__ __forceinline__ void umma_commit(void* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// 32 lanes x 32 consecutive columns of 32-bit accumulators -> 32 registers per thread.
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }
+__device__ __forceinline__ int min3(int a, int b, int c) { return min(min(a, b), c); }
+// (lo, hi) <- the two smallest of two sorted pairs
+__device__ __forceinline__ void merge2(int a1, int a2, int b1, int b2, int& lo, int& hi) {
+    lo = min(a1, b1);
+    hi = min3(max(a1, b1), a2, b2);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Per-column constants: c'_j = (||b_j||^2 << 8) | (j & 255); entries j >= n up to the tile
-// boundary get PAD_NORM so that the zero rows TMA fills in can never win.
-__global__ void __launch_bounds__(256)
-k_cprime(const uint8_t* __restrict__ d, int n, int n_padded, int* __restrict__ cprime) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_padded) return;
+// boundary get PAD_NORM so that the zero rows TMA fills in can never win.  One block = one tile of
+// 256 columns; it also records the smallest norm of each 128-column half (the epilogue's
+// conservative pre-filter needs a lower bound of ||b_j||^2 over the columns it is about to skip).
+__global__ void __launch_bounds__(BN)
+k_cprime(const uint8_t* __restrict__ d, int n, int n_padded, int* __restrict__ cprime, int* __restrict__ half_min) {
+    __shared__ int s_min[BN / 32];
+    const int j = blockIdx.x * BN + threadIdx.x;
     int nrm = PAD_NORM;
     if (j < n) {
         const uint4* p = reinterpret_cast<const uint4*>(d + (size_t)j * 128);
@@ -146,7 +152,16 @@ k_cprime(const uint8_t* __restrict__ d, int n, int n_padded, int* __restrict__ c
         }
         nrm = (int)s;
     }
-    cprime[j] = (nrm << 8) | (j & 255);
+    if (j < n_padded) cprime[j] = (nrm << 8) | (j & 255);
+    int m = nrm;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        const int* q = s_min + 4 * threadIdx.x;
+        half_min[2 * blockIdx.x + threadIdx.x] = min(min(q[0], q[1]), min(q[2], q[3]));
+    }
 }
 
 // Schedule: the m_tiles x n_tiles tile grid is flattened row-block-major and cut into gridDim.x
@@ -182,7 +197,8 @@ k_match_tc_merge(const int* __restrict__ part_idx, const int* __restrict__ part_
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_match_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int na, int nb,
-           const int* __restrict__ norms_a, const int* __restrict__ cprime_b, Sched sc,
+           const int* __restrict__ norms_a, const int* __restrict__ cprime_b, const int* __restrict__ half_min,
+           Sched sc,
            int* __restrict__ part_idx, int* __restrict__ part_d1, int* __restrict__ part_d2) {
     extern __shared__ uint8_t smem_raw[];
     // align to 1024 B (swizzle atom) with plain pointer arithmetic so the compiler keeps the shared space
@@ -263,7 +279,7 @@ k_match_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         // ===================== epilogue: top-2 straight out of TMEM =====================
         const int ew = warp - 2;
         const int quarter = warp & 3;        // TMEM lanes a warp may touch: 32 * (warp_id % 4)
-        const int half = ew >> 2;            // which 128 of the 256 columns
+        const int slice = ew >> 2;           // which SLICE columns of the 256
         const int row = quarter * 32 + lane; // row of the A tile == TMEM lane
         int* cp = S.cprime[ew];
         int acc = 0; uint32_t acc_phase = 0;
@@ -272,48 +288,60 @@ k_match_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             const int t1 = (int)min((long long)n_tiles, t0 + (r_end - seg));
             const int part = (int)blockIdx.x - sc.cta_of((long long)m_tile * n_tiles);
             int best = INT_MAX, second = INT_MAX, bj = 0;
-            int4 cnext = __ldg(reinterpret_cast<const int4*>(cprime_b + (size_t)t0 * BN + half * 128) + lane);
+            int2 cnext = __ldg(reinterpret_cast<const int2*>(cprime_b + (size_t)t0 * BN + slice * SLICE) + lane);
             for (int t = t0; t < t1; ++t) {
                 __syncwarp();
-                reinterpret_cast<int4*>(cp)[lane] = cnext;
+                reinterpret_cast<int2*>(cp)[lane] = cnext;
                 if (t + 1 < t1)
-                    cnext = __ldg(reinterpret_cast<const int4*>(cprime_b + (size_t)(t + 1) * BN + half * 128) + lane);
+                    cnext = __ldg(reinterpret_cast<const int2*>(cprime_b + (size_t)(t + 1) * BN + slice * SLICE) + lane);
+                // Pre-filter on the raw dot product: key_j = c'_j - 512 dot_j >= (nmin << 8) - 512 dot_j, so
+                // key_j < second  =>  dot_j > ((nmin << 8) - second) / 512 =: theta (floor keeps it safe).
+                const long long nmin8 = (long long)__ldg(half_min + 2 * t + (slice >> 1)) << 8;
+                int theta = (int)max((nmin8 - (long long)second) >> 9, -1ll);
+                const int best_in = best;
                 __syncwarp();
                 mbar_wait(&S.tmem_full[acc], acc_phase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 128);
-                const int best_in = best;
-                int v[2][32];
-                tmem_ld32(taddr, v[0]);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + slice * SLICE);
+                int v[2][16];
+                tmem_ld16(taddr, v[0]);
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
+                for (int ch = 0; ch < SLICE / 16; ++ch) {
                     tmem_ld_wait();
-                    if (ch < 3) {
-                        tmem_ld32(taddr + (ch + 1) * 32, v[(ch + 1) & 1]);
+                    if (ch < SLICE / 16 - 1) {
+                        tmem_ld16(taddr + (ch + 1) * 16, v[(ch + 1) & 1]);
                     } else {
                         // every accumulator value of this warp is in registers: hand the TMEM buffer back
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&S.tmem_empty[acc]);
                     }
-                    const int* vv = v[ch & 1];
+                    const int* w = v[ch & 1];
+                    const int g0 = max3(max3(w[0], w[1], w[2]), max3(w[3], w[4], w[5]), max(w[6], w[7]));
+                    const int g1 = max3(max3(w[8], w[9], w[10]), max3(w[11], w[12], w[13]), max(w[14], w[15]));
+                    if (max(g0, g1) > theta) {
+                        // rare after warm-up: some row of this warp may have a new top-2 column among these 16
 #pragma unroll
-                    for (int k = 0; k < 32; k += 8) {
-                        const int4 c0 = *reinterpret_cast<const int4*>(cp + ch * 32 + k);
-                        const int4 c1 = *reinterpret_cast<const int4*>(cp + ch * 32 + k + 4);
-                        int key[8];
-                        key[0] = vv[k] * -512 + c0.x; key[1] = vv[k + 1] * -512 + c0.y;
-                        key[2] = vv[k + 2] * -512 + c0.z; key[3] = vv[k + 3] * -512 + c0.w;
-                        key[4] = vv[k + 4] * -512 + c1.x; key[5] = vv[k + 5] * -512 + c1.y;
-                        key[6] = vv[k + 6] * -512 + c1.z; key[7] = vv[k + 7] * -512 + c1.w;
-                        const int mlo = min(min(key[0], key[1]), min(key[2], key[3]));
-                        const int mhi = min(min(key[4], key[5]), min(key[6], key[7]));
-                        if (min(mlo, mhi) < second) {  // rare after warm-up: a column enters this row's top 2
-                            // branch-free sorted insert, (best, second) <- two smallest of {best, second, key}
-#define SB_INS(kk) { const int t_ = max(best, (kk)); best = min(best, (kk)); second = min(second, t_); }
-                            if (mlo < second) { SB_INS(key[0]) SB_INS(key[1]) SB_INS(key[2]) SB_INS(key[3]) }
-                            if (mhi < second) { SB_INS(key[4]) SB_INS(key[5]) SB_INS(key[6]) SB_INS(key[7]) }
-#undef SB_INS
+                        for (int g = 0; g < 2; ++g) {
+                            if ((g == 0 ? g0 : g1) > theta) {
+                                const int* u = w + 8 * g;
+                                const int4 c0 = *reinterpret_cast<const int4*>(cp + ch * 16 + 8 * g);
+                                const int4 c1 = *reinterpret_cast<const int4*>(cp + ch * 16 + 8 * g + 4);
+                                const int k0 = u[0] * -512 + c0.x, k1 = u[1] * -512 + c0.y;
+                                const int k2 = u[2] * -512 + c0.z, k3 = u[3] * -512 + c0.w;
+                                const int k4 = u[4] * -512 + c1.x, k5 = u[5] * -512 + c1.y;
+                                const int k6 = u[6] * -512 + c1.z, k7 = u[7] * -512 + c1.w;
+                                // tournament: the two smallest of the eight keys (short dependency chains) ...
+                                int a1, a2, b1, b2, lo, hi;
+                                merge2(min(k0, k1), max(k0, k1), min(k2, k3), max(k2, k3), a1, a2);
+                                merge2(min(k4, k5), max(k4, k5), min(k6, k7), max(k6, k7), b1, b2);
+                                merge2(a1, a2, b1, b2, lo, hi);
+                                // ... merged into the row's running (best, second)
+                                const int nb_ = min(best, lo);
+                                second = min3(max(best, lo), second, hi);
+                                best = nb_;
+                                theta = (int)max((nmin8 - (long long)second) >> 9, -1ll);
+                            }
                         }
                     }
                 }
@@ -325,19 +353,24 @@ k_match_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
-            // ---- merge the two column halves of each row, add ||a||^2, store the segment's partial ----
-            if (half == 1) {
-                S.merge[row][0] = best; S.merge[row][1] = second; S.merge[row][2] = bj;
+            // ---- merge the column slices of each row, add ||a||^2, store the segment's partial ----
+            if (slice != 0) {
+                int* mg = S.merge[slice][row];
+                mg[0] = best; mg[1] = second; mg[2] = bj;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-            if (half == 0) {
-                const int ob = S.merge[row][0], os = S.merge[row][1], oj = S.merge[row][2];
+            if (slice == 0) {
                 int b = best, s2 = second, j = bj;
-                const int d0 = b >> 8, d1 = ob >> 8;
-                if (d1 < d0 || (d1 == d0 && oj < j)) {   // the other half wins: (distance, column) order
-                    s2 = min(os, b); b = ob; j = oj;
-                } else {
-                    s2 = min(s2, ob);
+#pragma unroll
+                for (int o = 1; o < EPI_WARPS / 4; ++o) {  // ascending column order within a tile
+                    const int* mg = S.merge[o][row];
+                    const int ob = mg[0], os = mg[1], oj = mg[2];
+                    const int d0 = b >> 8, d1 = ob >> 8;
+                    if (d1 < d0 || (d1 == d0 && oj < j)) {   // (distance, column) order
+                        s2 = min(os, b); b = ob; j = oj;
+                    } else {
+                        s2 = min(s2, ob);
+                    }
                 }
                 const int gi = m_tile * BM + row;
                 if (gi < na) {
@@ -403,14 +436,15 @@ cudaError_t launch_match_tc(const uint8_t* a, int na, const uint8_t* b, int nb, 
     if ((e = make_map(&map_b, b, nb, BN)) != cudaSuccess) return e;
     const int n_pad = match_tc_padded_rows(nb);
     if ((e = launch_norms(a, na, ms.norms_a, s)) != cudaSuccess) return e;
-    k_cprime<<<(n_pad + 255) / 256, 256, 0, s>>>(b, nb, n_pad, ms.norms_b);
+    int* half_min = ms.norms_b + n_pad;  // 2 ints per tile, right behind the per-column constants
+    k_cprime<<<n_pad / BN, BN, 0, s>>>(b, nb, n_pad, ms.norms_b, half_min);
     const int m_tiles = (na + BM - 1) / BM, n_tiles = n_pad / BN;
     Sched sc;
     sc.T = (long long)m_tiles * n_tiles;
     sc.n_tiles = n_tiles;
     // a row block may be cut into at most max_splits partials: G <= (max_splits - 1) * m_tiles
     sc.G = (int)min((long long)sm_count, min(sc.T, (long long)(ms.max_splits - 1) * m_tiles));
-    k_match_tc<<<sc.G, NTHREADS, kSmemBytes, s>>>(map_a, map_b, na, nb, ms.norms_a, ms.norms_b, sc, ms.part_idx,
+    k_match_tc<<<sc.G, NTHREADS, kSmemBytes, s>>>(map_a, map_b, na, nb, ms.norms_a, ms.norms_b, half_min, sc, ms.part_idx,
                                                    ms.part_d1, ms.part_d2);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     k_match_tc_merge<<<(na + 255) / 256, 256, 0, s>>>(ms.part_idx, ms.part_d1, ms.part_d2, sc, na, best_idx, best_d2,
