@@ -91,6 +91,7 @@ def load_library():
         "sift_b200_sync": (i32, [vp]),
         "sift_b200_stream": (vp, [vp]),
         "sift_b200_match_path": (i32, [i32, i32]),
+        "sift_b200_debug_options": (i32, [vp, i32, i32]),
         "sift_b200_debug_plane_dims": (i32, [vp, i32, i32p, i32p]),
         "sift_b200_debug_plane": (i32, [vp, i32, i32, i32, vp]),
         "sift_b200_debug_extrema": (i32, [vp, vp, i32, i32p]),
@@ -260,6 +261,9 @@ class SiftContext:
         return self._L.sift_b200_match_path(na, nb)
 
     # ---- introspection for the parity tests ----
+    def debug_options(self, keep_all_planes=False, unfused_pyramid=False):
+        self._check(self._L.sift_b200_debug_options(self._h, int(keep_all_planes), int(unfused_pyramid)))
+
     def plane_dims(self, octave):
         w, h = C.c_int(), C.c_int()
         self._check(self._L.sift_b200_debug_plane_dims(self._h, octave, C.byref(w), C.byref(h)))

@@ -54,6 +54,8 @@ struct sift_b200_ctx {
     bool have_result = false;
     int base_w = 0, base_h = 0;
     sift_b200_stats stats{};
+    bool keep_planes = false;    // also store G[4], G[5] (debug plane access)
+    bool force_unfused = false;  // per-level kernels instead of the fused octave cascade
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_stage;   // stage of the interval ending at event i (event 0: -1)
@@ -296,8 +298,19 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     CU(c, launch_blur(scratch, o0.G[0], nullptr, nullptr, bw, bh, o0.pitch, 0, 0, 0, taps[0], s));
     prof_mark(c, SIFT_B200_STAGE_INPUT, 2);
 
+    const bool fused = cascade_supported(taps) && !c->force_unfused;
     for (int o = 0; o < octaves; ++o) {
         OctaveDesc& od = c->pyr.oct[o];
+        if (fused) {
+            float* dec = nullptr;
+            int dw = 0, dh = 0, dp = 0;
+            if (o + 1 < octaves) {  // next base = G[3] decimated, sift.cpp:195-196
+                OctaveDesc& nx = c->pyr.oct[o + 1];
+                dec = nx.G[0]; dw = nx.w; dh = nx.h; dp = nx.pitch;
+            }
+            CU(c, launch_octave_fused(od, taps, dec, dw, dh, dp, c->keep_planes, s));
+            prof_mark(c, SIFT_B200_STAGE_PYRAMID, 2);
+        } else {
         for (int i = 1; i < kLayers; ++i) {
             float* dec = nullptr;
             int dw = 0, dh = 0, dp = 0;
@@ -308,6 +321,7 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
             CU(c, launch_blur(od.G[i - 1], od.G[i], od.D[i - 1], dec, od.w, od.h, od.pitch, dw, dh, dp, taps[i], s));
         }
         prof_mark(c, SIFT_B200_STAGE_PYRAMID, kLayers - 1);
+        }
         if (od.w >= 3 && od.h >= 3) {
             CU(c, launch_extrema(od, o, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, s));
             prof_mark(c, SIFT_B200_STAGE_EXTREMA, 1);
@@ -678,6 +692,13 @@ int sift_b200_sync(sift_b200_ctx* c) {
 void* sift_b200_stream(sift_b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 int sift_b200_match_path(int na, int nb) { return match_uses_tensor_cores(na, nb) ? 1 : 0; }
+
+int sift_b200_debug_options(sift_b200_ctx* c, int keep_all_planes, int unfused_pyramid) {
+    if (!c) return SIFT_B200_E_INVALID;
+    c->keep_planes = keep_all_planes != 0;
+    c->force_unfused = unfused_pyramid != 0;
+    return SIFT_B200_OK;
+}
 
 int sift_b200_debug_plane_dims(sift_b200_ctx* c, int octave, int* width, int* height) {
     if (!c || octave < 0 || octave >= c->pyr.octaves) return SIFT_B200_E_INVALID;

@@ -13,6 +13,10 @@ cudaError_t launch_prepare_f32(const float* src, int sw, int sh, int ch, float* 
 cudaError_t launch_blur(const float* in, float* out, float* dog, float* dec, int w, int h, int pitch,
                         int dec_w, int dec_h, int dec_pitch, const BlurTaps& taps, cudaStream_t s);
 
+bool cascade_supported(const BlurTaps* taps);
+cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, float* dec, int dec_w, int dec_h,
+                                int dec_pitch, bool keep_all, cudaStream_t s);
+
 // detect.cu
 struct SortScratch {
     int nb;             // number of x buckets (= output-frame image width)

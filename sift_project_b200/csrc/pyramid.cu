@@ -137,6 +137,247 @@ k_blur(const float* __restrict__ in, float* __restrict__ out, float* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused cascade: several consecutive levels of one octave per tile, intermediate levels staged in
+// shared memory only.  Two instantiations cover the reference's default scale space
+// (sift.cpp:143-155 -> radii 4,5,6,8,10):
+//   k_cascade<4,5,6>  G0 -> G1,G2,G3 (stored), D0,D1,D2, decimated next-octave base
+//   k_cascade<8,10,0> G3 -> (G4, G5 stay on chip) -> D3, D4
+// HBM traffic per octave pixel: 4 + 24 and 4 + 8 bytes (the algorithmic minimum is 36 + 1).
+// Tile = 128 x 64 outputs; the staged input carries the summed halo (rounded so that every
+// shared-memory row stays float4-aligned); each level is a horizontal pass smem -> smem and a
+// vertical pass smem -> smem (or -> registers -> HBM for the last level).
+// Clamp-to-edge semantics of every level (image.cpp:170-184): out-of-image positions of an
+// intermediate level must hold that level's edge value, not a blur of replicated input, so
+// border tiles re-replicate the edge after each intermediate level.
+// ------------------------------------------------------------------------------------------
+constexpr int CT = 512;  // threads per CTA of the fused kernel
+__host__ __device__ constexpr int ru4(int v) { return (v + 3) & ~3; }
+__host__ __device__ constexpr int ru2(int v) { return (v + 1) & ~1; }
+
+template <int R1, int R2, int R3>
+struct CascadeGeom {
+    static constexpr int NL = R3 > 0 ? 3 : 2;
+    static constexpr int HX2 = NL == 3 ? ru4(R3) : 0, HY2 = NL == 3 ? ru2(R3) : 0;  // halo kept around level 2
+    static constexpr int HX1 = ru4(HX2 + R2), HY1 = ru2(HY2 + R2);                  // ... around level 1
+    static constexpr int HX0 = ru4(HX1 + R1), HY0 = ru2(HY1 + R1);                  // ... around the input
+    static constexpr int W0 = TW + 2 * HX0, H0 = TH + 2 * HY0;
+    static constexpr int W1 = TW + 2 * HX1, H1 = TH + 2 * HY1;
+    static constexpr int W2 = TW + 2 * HX2, H2 = TH + 2 * HY2;
+    static constexpr int A_FLOATS = W0 * H0;   // input, later level 2
+    static constexpr int T_FLOATS = W1 * H0;   // horizontal-pass scratch (largest: level 1)
+    static constexpr int B_FLOATS = W1 * H1;   // level 1
+    static constexpr size_t kSmem = (size_t)(A_FLOATS + T_FLOATS + B_FLOATS) * sizeof(float);
+};
+
+struct CascadeArgs {
+    const float* in;      // level 0 of this launch (G0 or G3)
+    float* g[3];          // level outputs (nullable: not stored)
+    float* d[3];          // d[l] = level(l+1) - level(l)
+    float* dec;           // decimated copy of the LAST level (nullable)
+    int w, h, pitch;
+    int dec_w, dec_h, dec_pitch;
+    BlurTaps taps[3];
+};
+
+// horizontal pass: out[r][4q..4q+3] (width OUT_W) from in (width IN_W); OFF = x offset of the output
+// region inside the input region (a multiple of 4)
+template <int R, int IN_W, int OUT_W, int OFF>
+__device__ __forceinline__ void cascade_hpass(const float* __restrict__ in, float* __restrict__ out, int rows,
+                                              const BlurTaps& taps) {
+    constexpr int HXR = ru4(R);
+    constexpr int Q = OUT_W / 4;
+    for (int idx = threadIdx.x; idx < rows * Q; idx += CT) {
+        const int r = idx / Q, q = idx - r * Q;
+        const float4* src = reinterpret_cast<const float4*>(in + r * IN_W + OFF + 4 * q - HXR);
+        float v[4 + 2 * HXR];
+#pragma unroll
+        for (int k = 0; k < (4 + 2 * HXR) / 4; ++k) {
+            const float4 t = src[k];
+            v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+        }
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float acc = 0.f;
+#pragma unroll
+            for (int u = R; u >= 1; --u) acc = fmaf(taps.w[u], v[HXR + k - u] + v[HXR + k + u], acc);
+            o[k] = fmaf(taps.w[0], v[HXR + k], acc);
+        }
+        *reinterpret_cast<float4*>(out + r * OUT_W + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// vertical pass: 4 columns x 4 rows per item, streaming down 4 + 2R scratch rows; emit(r, q, acc[4])
+template <int R, int W, typename Emit>
+__device__ __forceinline__ void cascade_vpass(const float* __restrict__ tmp, int out_rows, const BlurTaps& taps,
+                                              Emit emit) {
+    constexpr int Q = W / 4;
+    for (int idx = threadIdx.x; idx < (out_rows / 4) * Q; idx += CT) {
+        const int g = idx / Q, q = idx - g * Q;
+        float4 acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 4 + 2 * R; ++r) {
+            const float4 t = *reinterpret_cast<const float4*>(tmp + (4 * g + r) * W + 4 * q);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int d = (r - k - R) < 0 ? (k + R - r) : (r - k - R);
+                if (d <= R) {
+                    const float wt = taps.w[d];
+                    acc[k].x = fmaf(wt, t.x, acc[k].x);
+                    acc[k].y = fmaf(wt, t.y, acc[k].y);
+                    acc[k].z = fmaf(wt, t.z, acc[k].z);
+                    acc[k].w = fmaf(wt, t.w, acc[k].w);
+                }
+            }
+        }
+        emit(4 * g, q, acc);
+    }
+}
+
+// re-replicate the image edge into the out-of-image part of a staged level (border tiles only)
+template <int W, int H>
+__device__ __forceinline__ void cascade_fix_edges(float* __restrict__ buf, int gx0, int gy0, int w, int h) {
+    for (int idx = threadIdx.x; idx < W * H; idx += CT) {
+        const int r = idx / W, c = idx - r * W;
+        const int gx = gx0 + c, gy = gy0 + r;
+        const int cx = min(max(gx, 0), w - 1), cy = min(max(gy, 0), h - 1);
+        if (cx != gx || cy != gy) buf[idx] = buf[(cy - gy0) * W + (cx - gx0)];
+    }
+}
+
+template <int R1, int R2, int R3>
+__global__ void __launch_bounds__(CT, 1) k_cascade(const CascadeArgs a) {
+    using G = CascadeGeom<R1, R2, R3>;
+    extern __shared__ __align__(16) float smem[];
+    float* sA = smem;
+    float* sT = sA + G::A_FLOATS;
+    float* sB = sT + G::T_FLOATS;
+    const int tid = threadIdx.x;
+    const int w = a.w, h = a.h, pitch = a.pitch;
+    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    const int gx0 = tx0 - G::HX0, gy0 = ty0 - G::HY0;
+    const bool interior = gx0 >= 0 && gy0 >= 0 && (tx0 + TW + G::HX0) <= w && (ty0 + TH + G::HY0) <= h;
+
+    // ---- stage the input tile (replicate padding == the reference's index clamping) ----
+    if (interior) {
+        constexpr int V = G::W0 / 4;
+        for (int idx = tid; idx < G::H0 * V; idx += CT) {
+            const int r = idx / V, c4 = idx - r * V;
+            cp_async16(sA + r * G::W0 + 4 * c4, a.in + (size_t)(gy0 + r) * pitch + gx0 + 4 * c4);
+        }
+        cp_async_wait_all();
+    } else {
+        for (int idx = tid; idx < G::H0 * G::W0; idx += CT) {
+            const int r = idx / G::W0, c = idx - r * G::W0;
+            const int gy = min(max(gy0 + r, 0), h - 1), gx = min(max(gx0 + c, 0), w - 1);
+            sA[idx] = __ldg(a.in + (size_t)gy * pitch + gx);
+        }
+    }
+    __syncthreads();
+
+    // store helper: 4 rows x 4 columns of a level and of its DoG against `prev` (shared memory)
+    auto store_level = [&](float* gout, float* dout, const float* prev, int prev_w, int prev_ox, int prev_oy,
+                           int y, int q, const float4 (&acc)[4], bool decimate) {
+        const int gx = tx0 + 4 * q;
+        if (gx >= w) return;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int gy = ty0 + y + k;
+            if (gy >= h) break;
+            const float4 o = acc[k];
+            if (gout != nullptr) *reinterpret_cast<float4*>(gout + (size_t)gy * pitch + gx) = o;
+            const float4 c = *reinterpret_cast<const float4*>(prev + (prev_oy + y + k) * prev_w + prev_ox + 4 * q);
+            *reinterpret_cast<float4*>(dout + (size_t)gy * pitch + gx) =
+                make_float4(o.x - c.x, o.y - c.y, o.z - c.z, o.w - c.w);
+            if (decimate && a.dec != nullptr && !(gy & 1)) {
+                const int dy = gy >> 1, dx = gx >> 1;
+                if (dy < a.dec_h) {
+                    if (dx + 1 < a.dec_w)
+                        *reinterpret_cast<float2*>(a.dec + (size_t)dy * a.dec_pitch + dx) = make_float2(o.x, o.z);
+                    else if (dx < a.dec_w)
+                        a.dec[(size_t)dy * a.dec_pitch + dx] = o.x;
+                }
+            }
+        }
+    };
+
+    // ---- level 1: sA -> sT -> sB ----
+    cascade_hpass<R1, G::W0, G::W1, G::HX0 - G::HX1>(sA, sT, G::H0, a.taps[0]);
+    __syncthreads();
+    cascade_vpass<R1, G::W1>(sT + (G::HY0 - G::HY1 - R1) * G::W1, G::H1, a.taps[0],
+                             [&](int y, int q, const float4 (&acc)[4]) {
+#pragma unroll
+                                 for (int k = 0; k < 4; ++k)
+                                     *reinterpret_cast<float4*>(sB + (y + k) * G::W1 + 4 * q) = acc[k];
+                             });
+    __syncthreads();
+    // emit the centre of level 1 (+ DoG against the input centre)
+    for (int idx = tid; idx < (TH / 4) * (TW / 4); idx += CT) {
+        const int g = idx / (TW / 4), q = idx - g * (TW / 4);
+        float4 acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            acc[k] = *reinterpret_cast<const float4*>(sB + (G::HY1 + 4 * g + k) * G::W1 + G::HX1 + 4 * q);
+        store_level(a.g[0], a.d[0], sA, G::W0, G::HX0, G::HY0, 4 * g, q, acc, false);
+    }
+    if (!interior) {
+        __syncthreads();
+        cascade_fix_edges<G::W1, G::H1>(sB, tx0 - G::HX1, ty0 - G::HY1, w, h);
+    }
+    __syncthreads();
+
+    if (G::NL == 3) {
+        // ---- level 2: sB -> sT -> sA (the input is dead by now) ----
+        cascade_hpass<R2, G::W1, G::W2, G::HX1 - G::HX2>(sB, sT, G::H1, a.taps[1]);
+        __syncthreads();
+        cascade_vpass<R2, G::W2>(sT + (G::HY1 - G::HY2 - R2) * G::W2, G::H2, a.taps[1],
+                                 [&](int y, int q, const float4 (&acc)[4]) {
+#pragma unroll
+                                     for (int k = 0; k < 4; ++k)
+                                         *reinterpret_cast<float4*>(sA + (y + k) * G::W2 + 4 * q) = acc[k];
+                                 });
+        __syncthreads();
+        for (int idx = tid; idx < (TH / 4) * (TW / 4); idx += CT) {
+            const int g = idx / (TW / 4), q = idx - g * (TW / 4);
+            float4 acc[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                acc[k] = *reinterpret_cast<const float4*>(sA + (G::HY2 + 4 * g + k) * G::W2 + G::HX2 + 4 * q);
+            store_level(a.g[1], a.d[1], sB, G::W1, G::HX1, G::HY1, 4 * g, q, acc, false);
+        }
+        if (!interior) {
+            __syncthreads();
+            cascade_fix_edges<G::W2, G::H2>(sA, tx0 - G::HX2, ty0 - G::HY2, w, h);
+        }
+        __syncthreads();
+        // ---- level 3: sA -> sT -> registers -> HBM ----
+        cascade_hpass<(R3 > 0 ? R3 : 1), G::W2, TW, G::HX2>(sA, sT, G::H2, a.taps[2]);
+        __syncthreads();
+        cascade_vpass<(R3 > 0 ? R3 : 1), TW>(sT + (G::HY2 - R3) * TW, TH, a.taps[2],
+                                           [&](int y, int q, const float4 (&acc)[4]) {
+                                               store_level(a.g[2], a.d[2], sA, G::W2, G::HX2, G::HY2, y, q, acc, true);
+                                           });
+    } else {
+        // ---- two-level variant: level 2 is the last: sB -> sT -> registers -> HBM ----
+        cascade_hpass<R2, G::W1, TW, G::HX1>(sB, sT, G::H1, a.taps[1]);
+        __syncthreads();
+        cascade_vpass<R2, TW>(sT + (G::HY1 - R2) * TW, TH, a.taps[1],
+                              [&](int y, int q, const float4 (&acc)[4]) {
+                                  store_level(a.g[1], a.d[1], sB, G::W1, G::HX1, G::HY1, y, q, acc, true);
+                              });
+    }
+}
+
+template <int R1, int R2, int R3>
+cudaError_t launch_cascade_t(const CascadeArgs& a, cudaStream_t s) {
+    dim3 grid((a.w + TW - 1) / TW, (a.h + TH - 1) / TH);
+    k_cascade<R1, R2, R3><<<grid, CT, CascadeGeom<R1, R2, R3>::kSmem, s>>>(a);
+    return cudaGetLastError();
+}
+
 // Input stage: (RGB ->) gray, optional 2x bilinear with the reference's right/bottom clamp.
 // u8 gray input is exact in FP32 (weights 0, 1/2, 1/4 of integers); everything else is formed in
 // FP64 with the reference's association order and rounded once.
@@ -206,6 +447,10 @@ cudaError_t init_blur_r() {
 // Per-device one-time setup (opt-in to > 48 KB dynamic shared memory); called by context creation.
 cudaError_t pyramid_init() {
     cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_cascade<4, 5, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)CascadeGeom<4, 5, 6>::kSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_cascade<8, 10, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)CascadeGeom<8, 10, 0>::kSmem)) != cudaSuccess) return e;
 #define SB_INIT(R) if ((e = init_blur_r<R>()) != cudaSuccess) return e;
     SB_INIT(1) SB_INIT(2) SB_INIT(3) SB_INIT(4) SB_INIT(5) SB_INIT(6) SB_INIT(7) SB_INIT(8)
     SB_INIT(9) SB_INIT(10) SB_INIT(11) SB_INIT(12)
@@ -223,6 +468,34 @@ cudaError_t launch_blur(const float* in, float* out, float* dog, float* dec, int
         default: return cudaErrorInvalidValue;
     }
 #undef SB_CASE
+}
+
+// The fused per-octave path exists for the reference's default radii (4,5,6 | 8,10).
+bool cascade_supported(const BlurTaps* taps) {
+    return taps[1].radius == 4 && taps[2].radius == 5 && taps[3].radius == 6 && taps[4].radius == 8 &&
+           taps[5].radius == 10;
+}
+
+// One octave: G[0] -> G[1..3], D[0..4], next base.  keep_all also stores G[4], G[5] (debug planes).
+cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, float* dec, int dec_w, int dec_h,
+                                int dec_pitch, bool keep_all, cudaStream_t s) {
+    CascadeArgs a;
+    a.in = od.G[0];
+    a.g[0] = od.G[1]; a.g[1] = od.G[2]; a.g[2] = od.G[3];
+    a.d[0] = od.D[0]; a.d[1] = od.D[1]; a.d[2] = od.D[2];
+    a.dec = dec; a.dec_w = dec_w; a.dec_h = dec_h; a.dec_pitch = dec_pitch;
+    a.w = od.w; a.h = od.h; a.pitch = od.pitch;
+    a.taps[0] = taps[1]; a.taps[1] = taps[2]; a.taps[2] = taps[3];
+    cudaError_t e = launch_cascade_t<4, 5, 6>(a, s);
+    if (e != cudaSuccess) return e;
+    CascadeArgs b;
+    b.in = od.G[3];
+    b.g[0] = keep_all ? od.G[4] : nullptr; b.g[1] = keep_all ? od.G[5] : nullptr; b.g[2] = nullptr;
+    b.d[0] = od.D[3]; b.d[1] = od.D[4]; b.d[2] = nullptr;
+    b.dec = nullptr; b.dec_w = b.dec_h = b.dec_pitch = 0;
+    b.w = od.w; b.h = od.h; b.pitch = od.pitch;
+    b.taps[0] = taps[4]; b.taps[1] = taps[5]; b.taps[2] = taps[5];
+    return launch_cascade_t<8, 10, 0>(b, s);
 }
 
 cudaError_t launch_prepare_u8(const uint8_t* src, int sw, int sh, int ch, float* dst, int dw, int dh,

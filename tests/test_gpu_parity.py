@@ -49,7 +49,9 @@ def test_pyramid_planes_match_oracle(ctx, synth):
     """Every Gaussian and DoG plane of every octave vs the FP64 oracle (image.cpp:156-238,
     sift.cpp:161-225).  FP32 storage: a few ulp of 255."""
     img = synth["image"]
+    ctx.debug_options(keep_all_planes=True)   # the fused octave kernel keeps G4, G5 on chip otherwise
     ctx.detect(img)
+    ctx.debug_options()
     run = O.Run(O.port(), img, keep_pyramid=True)
     st = ctx.stats()
     assert st["octaves"] == run.octaves == 7
@@ -338,3 +340,23 @@ def test_match_large_tc_vs_simt(ctx, force_path):
         out[path] = (idx.cpu().numpy(), d1.cpu().numpy(), d2.cpu().numpy())
     for x, y in zip(out["tc"], out["simt"]):
         assert np.array_equal(x, y)
+
+
+def test_fused_octave_cascade_equals_per_level_kernels(ctx):
+    """The fused per-octave cascade (k_cascade) and the one-kernel-per-level path run the same
+    arithmetic in the same order: every plane and the final records are bit-identical, including
+    image sizes that are not multiples of the tile and octaves smaller than one tile."""
+    for h, w, seed in ((192, 256, 42), (301, 517, 7), (97, 1030, 8), (768, 1024, 9)):
+        img = O.synth_image(h, w, seed=seed)
+        ctx.debug_options(keep_all_planes=True, unfused_pyramid=True)
+        ref = ctx.detect(img)
+        octs = ctx.stats()["octaves"]
+        planes = [[ctx.gaussian(o, l) for l in range(6)] + [ctx.dog(o, l) for l in range(5)] for o in range(octs)]
+        ctx.debug_options(keep_all_planes=True, unfused_pyramid=False)
+        got = ctx.detect(img)
+        for o in range(octs):
+            mine = [ctx.gaussian(o, l) for l in range(6)] + [ctx.dog(o, l) for l in range(5)]
+            for k, (x, y) in enumerate(zip(mine, planes[o])):
+                assert np.array_equal(x, y), (h, w, o, k, float(np.abs(x - y).max()))
+        assert got.tobytes() == ref.tobytes(), (h, w)
+    ctx.debug_options()
