@@ -374,6 +374,39 @@ def run_b200(args):
                 "whole_detect": {"algorithmic_bytes": HBM_BYTES_PER_INPUT_PIXEL * W * H, "ms": total_ms,
                                  "frac": HBM_BYTES_PER_INPUT_PIXEL * W * H / (total_ms * 1e-3) / 1e9 / hbm_peak}}
 
+    # ---- the matcher (the only tensor-core stage): one 20k x 20k pair of config 5, device-resident ----
+    match = None
+    if rank == 0:
+        def synth_desc(n, seed):
+            g = torch.Generator(device=dev); g.manual_seed(seed)
+            hh = torch.randn((n, 128), generator=g, device=dev).abs()
+            hh = hh / hh.norm(dim=1, keepdim=True)
+            hh = hh.clamp(max=0.2)
+            hh = hh / hh.norm(dim=1, keepdim=True)
+            return torch.floor(512.0 * hh).clamp(max=255).to(torch.uint8).contiguous()
+        nm = 20000
+        da, db = synth_desc(nm, 1234), synth_desc(nm, 1235)
+        mi = torch.empty(nm, dtype=torch.int32, device=dev); m1 = torch.empty_like(mi); m2 = torch.empty_like(mi)
+        torch.cuda.synchronize()
+        c0 = ctxs[0]
+        for _ in range(5):
+            c0.match_enqueue(da, nm, db, nm, mi, m1, m2)
+        c0.sync()
+        reps = 50
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(streams[0])
+        for _ in range(reps):
+            c0.match_enqueue(da, nm, db, nm, mi, m1, m2)
+        e1.record(streams[0])
+        c0.sync()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        tf = 2.0 * nm * nm * 128 / (us * 1e-6) / 1e12
+        tpeak = peaks.get("bf16_tflops") or 1590.0
+        match = {"workload": "20000 x 20000 x 128 u8 descriptors, top-2 + norms fused (tcgen05 kind::i8)",
+                 "us_per_pair": us, "tflops_equivalent": tf, "peak_bf16_tflops": tpeak, "frac_of_bf16_peak": tf / tpeak,
+                 "path": "tcgen05" if c0.match_path(nm, nm) else "simt", "data_in_l2": True,
+                 "note": "2*N1*N2*128 / t; both descriptor sets (5 MB) are L2-resident by construction of the problem"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -395,7 +428,7 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_step,
                     "d2h_bytes_per_step": d2h_step, "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "stages_ms": stages, "stage_launches": stage_launches,
+            "stages_ms": stages, "stage_launches": stage_launches, "match": match,
         }
         print(json.dumps(line))
     for c in ctxs:

@@ -289,6 +289,10 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     // reaches it), then the initial blur into G[0].
     OctaveDesc& o0 = c->pyr.oct[0];
     float* scratch = o0.G[5];
+    if (sizeof(T) == 1 && input_fused_supported(channels, taps[0]) && !c->force_unfused) {
+        CU(c, launch_input_u8((const uint8_t*)d_pixels, width, height, o0.G[0], bw, bh, o0.pitch, doubled, taps[0], s));
+        prof_mark(c, SIFT_B200_STAGE_INPUT, 1);
+    } else {
     if (sizeof(T) == 1)
         CU(c, launch_prepare_u8((const uint8_t*)d_pixels, width, height, channels, scratch, bw, bh, o0.pitch,
                                 doubled, s));
@@ -297,6 +301,7 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
                                  doubled, s));
     CU(c, launch_blur(scratch, o0.G[0], nullptr, nullptr, bw, bh, o0.pitch, 0, 0, 0, taps[0], s));
     prof_mark(c, SIFT_B200_STAGE_INPUT, 2);
+    }
 
     const bool fused = cascade_supported(taps) && !c->force_unfused;
     for (int o = 0; o < octaves; ++o) {

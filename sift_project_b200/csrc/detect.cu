@@ -15,6 +15,17 @@ namespace sb {
 namespace {
 
 __device__ __forceinline__ float ldg(const float* p) { return __ldg(p); }
+// three-input FP32 min / max (FMNMX3, sm_100)
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
 
 // ------------------------------------------------------------------------------------------
 // Extrema scan -- sift.cpp:264-291 (detect_octave_extrema) + :227-256 (is_extremum).
@@ -23,11 +34,24 @@ __device__ __forceinline__ float ldg(const float* p) { return __ldg(p); }
 // One warp walks a 30-column strip downwards: each lane loads only its own column, the 3-wide
 // row min/max come from warp shuffles, the 3-tall window lives in registers.
 // ------------------------------------------------------------------------------------------
-constexpr int EX_ROWS = 16;  // output rows per warp
+// warp-aggregated, order-free append of the hits of one ballot (the list is sorted later)
+__device__ __noinline__ void extrema_emit(unsigned m, bool hit, int lane, int x, int y, int z, int octave,
+                                          Cand* __restrict__ cands, int cap, Counters* __restrict__ counters) {
+    int slot0 = 0;
+    if (lane == 0) slot0 = atomicAdd(&counters->n_extrema, __popc(m));
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    if (hit) {
+        const int slot = slot0 + __popc(m & ((1u << lane) - 1));
+        if (slot < cap) cands[slot] = Cand{x, y, z, octave};
+    }
+}
 
-__global__ void __launch_bounds__(256)
+constexpr int EX_ROWS = 32;  // output rows per warp
+
+__global__ void __launch_bounds__(256, 4)
 k_extrema(const OctaveDesc oct, int octave, float thr, Cand* __restrict__ cands, int cap,
           Counters* __restrict__ counters) {
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w = oct.w, h = oct.h, pitch = oct.pitch;
     const int x = blockIdx.x * 30 + lane;                       // lanes 1..30 produce output
@@ -36,53 +60,52 @@ k_extrema(const OctaveDesc oct, int octave, float thr, Cand* __restrict__ cands,
     const int xc = min(x, w - 1);
     const bool lane_out = lane >= 1 && lane <= 30 && x <= w - 2;
 
-    float hmin[kDogs][3], hmax[kDogs][3], ctr[kDogs][3];
-    auto load_row = [&](int y, int slot) {
+    // 3 rotating window rows per plane: min / max over x-1..x+1, and the centre of planes 1..3
+    float hmin[kDogs][3], hmax[kDogs][3], ctr[3][3];
+    float raw[3][kDogs];  // rows loaded two iterations ahead of their use (bytes in flight hide HBM latency)
+    auto fetch = [&](int y, int rs) {
         const int yc = min(y, h - 1);
 #pragma unroll
+        for (int z = 0; z < kDogs; ++z) raw[rs][z] = ldg(oct.D[z] + (size_t)yc * pitch + xc);
+    };
+    auto absorb = [&](int slot, int rs) {
+#pragma unroll
         for (int z = 0; z < kDogs; ++z) {
-            const float v = ldg(oct.D[z] + (size_t)yc * pitch + xc);
-            const float l = __shfl_up_sync(0xffffffffu, v, 1), r = __shfl_down_sync(0xffffffffu, v, 1);
-            hmin[z][slot] = fminf(v, fminf(l, r));
-            hmax[z][slot] = fmaxf(v, fmaxf(l, r));
-            ctr[z][slot] = v;
+            const float v = raw[rs][z];
+            const float l = __shfl_up_sync(FULL, v, 1), r = __shfl_down_sync(FULL, v, 1);
+            hmin[z][slot] = fmin3(v, l, r);
+            hmax[z][slot] = fmax3(v, l, r);
+            if (z >= 1 && z <= 3) ctr[z - 1][slot] = v;
         }
     };
-    load_row(ys - 1, 0);
-    load_row(ys, 1);
+    fetch(ys - 1, 0); fetch(ys, 1); fetch(ys + 1, 2);
+    absorb(0, 0);
+    fetch(ys + 2, 0);
+    absorb(1, 1);
 #pragma unroll 1
-    for (int k = 0; k < EX_ROWS; ++k) {
-        const int y = ys + k;
-        if (y > h - 2) break;
-        load_row(y + 1, 2);
-        float vmin[kDogs], vmax[kDogs];
+    for (int k0 = 0; k0 < EX_ROWS + 2; k0 += 3) {
 #pragma unroll
-        for (int z = 0; z < kDogs; ++z) {
-            vmin[z] = fminf(hmin[z][0], fminf(hmin[z][1], hmin[z][2]));
-            vmax[z] = fmaxf(hmax[z][0], fmaxf(hmax[z][1], hmax[z][2]));
-        }
+        for (int kj = 0; kj < 3; ++kj) {  // unrolled by the window height: slot rotation without moves
+            const int y = ys + k0 + kj;
+            if (k0 + kj >= EX_ROWS || y > h - 2) break;
+            const int mid = (kj + 1) % 3;
+            absorb((kj + 2) % 3, (kj + 2) % 3);   // row y + 1 (fetched two iterations ago)
+            fetch(y + 3, (kj + 1) % 3);           // in flight while this and the next row are tested
+            float vmin[kDogs], vmax[kDogs];
 #pragma unroll
-        for (int z = 1; z <= 3; ++z) {
-            const float c = ctr[z][1];
-            const float mx = fmaxf(vmax[z - 1], fmaxf(vmax[z], vmax[z + 1]));
-            const float mn = fminf(vmin[z - 1], fminf(vmin[z], vmin[z + 1]));
-            const bool hit = lane_out && fabsf(c) > thr && (c == mx || c == mn);
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&counters->n_extrema, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (hit) {
-                    const int slot = base + __popc(m & ((1u << lane) - 1));
-                    if (slot < cap) cands[slot] = Cand{x, y, z, octave};
-                }
+            for (int z = 0; z < kDogs; ++z) {
+                vmin[z] = fmin3(hmin[z][0], hmin[z][1], hmin[z][2]);
+                vmax[z] = fmax3(hmax[z][0], hmax[z][1], hmax[z][2]);
             }
-        }
 #pragma unroll
-        for (int z = 0; z < kDogs; ++z) {
-            hmin[z][0] = hmin[z][1]; hmin[z][1] = hmin[z][2];
-            hmax[z][0] = hmax[z][1]; hmax[z][1] = hmax[z][2];
-            ctr[z][0] = ctr[z][1]; ctr[z][1] = ctr[z][2];
+            for (int z = 1; z <= 3; ++z) {
+                const float cv = ctr[z - 1][mid];
+                const float mx = fmax3(vmax[z - 1], vmax[z], vmax[z + 1]);
+                const float mn = fmin3(vmin[z - 1], vmin[z], vmin[z + 1]);
+                const bool hit = lane_out && fabsf(cv) > thr && (cv == mx || cv == mn);
+                const unsigned m = __ballot_sync(FULL, hit);
+                if (m) extrema_emit(m, hit, lane, x, y, z, octave, cands, cap, counters);
+            }
         }
     }
 }
@@ -191,7 +214,9 @@ __global__ void __launch_bounds__(256, 2)
 k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, KpCore* __restrict__ oriented,
          Counters* __restrict__ counters, const StageParams sp) {
     __shared__ unsigned s_hist[8][ORI_COPIES][kOriBins];
+    __shared__ double s_smooth[8][kOriBins];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* smooth = s_smooth[warp];
     const int n = min(counters->n_raw, sp.cap_raw);
     unsigned* hist = &s_hist[warp][0][0];
     unsigned* my_hist = s_hist[warp][lane & (ORI_COPIES - 1)];
@@ -232,32 +257,60 @@ k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, Kp
             atomicAdd(&my_hist[b], __float2uint_rn(wgt * mag * fix));
         }
         __syncwarp();
+        // lane 0 smooths (the reference's in-place, sequential 1/4-1/2-1/4 filter, sift.cpp:496-504:
+        // bin i sees the already-updated bin i-1, and bin 35 the already-updated bin 0), fully
+        // unrolled so the 36 values stay in registers; all lanes then test their bins for peaks.
         if (lane == 0) {
             double hd[kOriBins];
+#pragma unroll
             for (int b = 0; b < kOriBins; ++b) {
                 unsigned long long t = 0;
 #pragma unroll
                 for (int cpy = 0; cpy < ORI_COPIES; ++cpy) t += hist[cpy * kOriBins + b];
                 hd[b] = (double)t * unfix;
             }
-            for (int it = 0; it < 2; ++it)  // ORI_SMOOTH_ITERATIONS; in place, sequential
+#pragma unroll
+            for (int it = 0; it < 2; ++it)  // ORI_SMOOTH_ITERATIONS
+#pragma unroll
                 for (int b = 0; b < kOriBins; ++b)
-                    hd[b] = 0.25 * hd[(b - 1 + kOriBins) % kOriBins] + 0.5 * hd[b] +
-                            0.25 * hd[(b + 1) % kOriBins];
-            double top = hd[0];
-            for (int b = 1; b < kOriBins; ++b) top = fmax(top, hd[b]);
-            for (int b = 0; b < kOriBins; ++b) {
-                const double h0 = hd[(b - 1 + kOriBins) % kOriBins], h1 = hd[b], h2 = hd[(b + 1) % kOriBins];
-                if (!(h1 > h0 && h1 > h2 && h1 > (sp.peak_ratio * top))) continue;
-                double pos = b + 0.5 * (h0 - h2) / (h0 - 2 * h1 + h2);
-                pos = fmod(pos + kOriBins, (double)kOriBins);
-                double ori = kTwoPi * pos / kOriBins;
-                ori = fmod(ori + kTwoPi, kTwoPi);
-                KpCore out = kp;
-                out.pori = ori;
-                if (sp.doubled) { out.x /= 2; out.y /= 2; out.size /= 2; }
-                const int slot = atomicAdd(&counters->n_oriented, 1);
-                if (slot < sp.cap_oriented) oriented[slot] = out;
+                    hd[b] = 0.25 * hd[(b + kOriBins - 1) % kOriBins] + 0.5 * hd[b] + 0.25 * hd[(b + 1) % kOriBins];
+#pragma unroll
+            for (int b = 0; b < kOriBins; ++b) smooth[b] = hd[b];
+        }
+        __syncwarp();
+        double top = fmax(smooth[lane], (lane + 32 < kOriBins) ? smooth[lane + 32] : 0.0);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) top = fmax(top, __shfl_xor_sync(0xffffffffu, top, d));
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep) {
+            const int b = lane + 32 * rep;
+            bool peak = false;
+            double ori = 0.0;
+            if (b < kOriBins) {
+                const double h0 = smooth[(b + kOriBins - 1) % kOriBins], h1 = smooth[b], h2 = smooth[(b + 1) % kOriBins];
+                if (h1 > h0 && h1 > h2 && h1 > (sp.peak_ratio * top)) {
+                    peak = true;
+                    // fmod(t, m) for t in [0, 2m) is t or t - m, both exact
+                    double pos = (double)b + 0.5 * (h0 - h2) / (h0 - 2 * h1 + h2);
+                    pos = pos + (double)kOriBins;
+                    if (pos >= (double)kOriBins) pos -= (double)kOriBins;
+                    ori = kTwoPi * pos / kOriBins;
+                    ori = ori + kTwoPi;
+                    if (ori >= kTwoPi) ori -= kTwoPi;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, peak);
+            if (m) {
+                int slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(&counters->n_oriented, __popc(m));
+                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                if (peak) {
+                    const int slot = slot0 + __popc(m & ((1u << lane) - 1));
+                    KpCore out = kp;
+                    out.pori = ori;
+                    if (sp.doubled) { out.x /= 2; out.y /= 2; out.size /= 2; }
+                    if (slot < sp.cap_oriented) oriented[slot] = out;
+                }
             }
         }
         __syncwarp();

@@ -378,6 +378,55 @@ cudaError_t launch_cascade_t(const CascadeArgs& a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused input stage for 8-bit gray images: resize_inter_bilinear(2,2) (image.cpp:62-88, optional)
+// + the initial blur (sift.cpp:124, radius 4) in one pass: the up-sampled tile is formed in shared
+// memory straight from the u8 pixels (exact in FP32: quarter-integers), blurred, and only G[0][0]
+// is written.  Reads 1 byte, writes 16 bytes per input pixel instead of 4 + 32 + 16.
+// ------------------------------------------------------------------------------------------
+constexpr int IN_R = 4;
+constexpr int IN_W0 = TW + 2 * IN_R, IN_H0 = TH + 2 * IN_R;
+constexpr size_t kInputSmem = (size_t)(IN_W0 * IN_H0 + TW * IN_H0) * sizeof(float);
+
+template <bool DOUBLED>
+__global__ void __launch_bounds__(CT, 2)
+k_input_u8(const uint8_t* __restrict__ src, int sw, int sh, float* __restrict__ dst, int w, int h, int pitch,
+           const BlurTaps taps) {
+    extern __shared__ __align__(16) float smem[];
+    float* sA = smem;
+    float* sT = smem + IN_W0 * IN_H0;
+    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    for (int idx = threadIdx.x; idx < IN_W0 * IN_H0; idx += CT) {
+        const int r = idx / IN_W0, c = idx - r * IN_W0;
+        const int X = min(max(tx0 - IN_R + c, 0), w - 1), Y = min(max(ty0 - IN_R + r, 0), h - 1);
+        float v;
+        if (DOUBLED) {
+            const int x0 = X >> 1, y0 = Y >> 1;
+            const int x1 = min(x0 + 1, sw - 1), y1 = min(y0 + 1, sh - 1);
+            const float fx = (X & 1) ? 0.5f : 0.0f, fy = (Y & 1) ? 0.5f : 0.0f;
+            const float p = __ldg(src + (size_t)y0 * sw + x0), q = __ldg(src + (size_t)y0 * sw + x1);
+            const float t = __ldg(src + (size_t)y1 * sw + x0), u = __ldg(src + (size_t)y1 * sw + x1);
+            const float top = p * (1.f - fx) + q * fx, bot = t * (1.f - fx) + u * fx;
+            v = top * (1.f - fy) + bot * fy;
+        } else {
+            v = (float)__ldg(src + (size_t)Y * sw + X);
+        }
+        sA[idx] = v;
+    }
+    __syncthreads();
+    cascade_hpass<IN_R, IN_W0, TW, IN_R>(sA, sT, IN_H0, taps);
+    __syncthreads();
+    cascade_vpass<IN_R, TW>(sT, TH, taps, [&](int y, int q, const float4 (&acc)[4]) {
+        const int gx = tx0 + 4 * q;
+        if (gx >= w) return;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int gy = ty0 + y + k;
+            if (gy < h) *reinterpret_cast<float4*>(dst + (size_t)gy * pitch + gx) = acc[k];
+        }
+    });
+}
+
 // Input stage: (RGB ->) gray, optional 2x bilinear with the reference's right/bottom clamp.
 // u8 gray input is exact in FP32 (weights 0, 1/2, 1/4 of integers); everything else is formed in
 // FP64 with the reference's association order and rounded once.
@@ -447,6 +496,10 @@ cudaError_t init_blur_r() {
 // Per-device one-time setup (opt-in to > 48 KB dynamic shared memory); called by context creation.
 cudaError_t pyramid_init() {
     cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_input_u8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kInputSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_input_u8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kInputSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_cascade<4, 5, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)CascadeGeom<4, 5, 6>::kSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_cascade<8, 10, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -468,6 +521,19 @@ cudaError_t launch_blur(const float* in, float* out, float* dog, float* dec, int
         default: return cudaErrorInvalidValue;
     }
 #undef SB_CASE
+}
+
+// u8 gray input -> G[0][0] (up-sample + initial blur); taps.radius must be 4
+bool input_fused_supported(int channels, const BlurTaps& taps) { return channels == 1 && taps.radius == IN_R; }
+
+cudaError_t launch_input_u8(const uint8_t* src, int sw, int sh, float* dst, int w, int h, int pitch, int doubled,
+                            const BlurTaps& taps, cudaStream_t s) {
+    dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH);
+    if (doubled)
+        k_input_u8<true><<<grid, CT, kInputSmem, s>>>(src, sw, sh, dst, w, h, pitch, taps);
+    else
+        k_input_u8<false><<<grid, CT, kInputSmem, s>>>(src, sw, sh, dst, w, h, pitch, taps);
+    return cudaGetLastError();
 }
 
 // The fused per-octave path exists for the reference's default radii (4,5,6 | 8,10).
