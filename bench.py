@@ -228,6 +228,8 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (no "NCCL version" banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -430,7 +432,7 @@ def run_b200(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "stages_ms": stages, "stage_launches": stage_launches, "match": match,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     for c in ctxs:
         c.close()
     if world > 1:
