@@ -248,7 +248,8 @@ k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, Kp
             const float* c = img + (size_t)(y + j_off) * pitch + (x + i_off);
             const float dx = ldg(c + 1) - ldg(c - 1);
             const float dy = ldg(c - pitch) - ldg(c + pitch);  // up minus down, sift.cpp:483
-            const float mag = sqrtf(dx * dx + dy * dy);
+            const float g2 = dx * dx + dy * dy;
+            const float mag = g2 > 0.f ? g2 * rsqrtf(g2) : 0.f;
             const float ang = atan2f(dy, dx);
             const float wgt = __expf((float)(i_off * i_off + j_off * j_off) * neg_inv_denom);
             int b = (int)roundf((float)kOriBins * (ang + 3.14159265358979323846f) * (1.0f / 6.283185307179586f));
@@ -463,19 +464,22 @@ __global__ void __launch_bounds__(256) k_bucket_gather(SortScratch ss) {
 // FP64 normalise / clamp 0.2 / renormalise / floor(512 x) / min 255.  Writes the 168-byte record
 // and the dense 128-byte row.
 // ------------------------------------------------------------------------------------------
-constexpr int DESC_COPIES = 2;
+constexpr int DESC_COPIES = 2;   // odd / even lanes (8 copies x 4 warps measured slower: occupancy)
+constexpr int DESC_WARPS = 8;    // warps (= keypoints in flight) per CTA
+constexpr int DESC_GRID = 6;                            // 4x4 cells + a one-cell border that absorbs dropped bins
+constexpr int DESC_WORDS = DESC_GRID * DESC_GRID * 8;   // per histogram copy
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(DESC_WARPS * 32)
 k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ oriented,
            const int* __restrict__ final_order, const Counters* __restrict__ counters,
            uint8_t* __restrict__ records, uint8_t* __restrict__ desc, int cap_final, const StageParams sp) {
-    __shared__ unsigned s_hist[8][DESC_COPIES][128];
+    __shared__ unsigned s_hist[DESC_WARPS][DESC_COPIES][DESC_WORDS];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned* hist = &s_hist[warp][0][0];
     unsigned* my_hist = s_hist[warp][lane & (DESC_COPIES - 1)];
     const int n = min(counters->n_final, cap_final);
-    for (int i = blockIdx.x * 8 + warp; i < n; i += gridDim.x * 8) {
+    for (int i = blockIdx.x * DESC_WARPS + warp; i < n; i += gridDim.x * DESC_WARPS) {
         const KpCore kp = oriented[final_order[i]];
         const OctaveDesc& oc = pyr->oct[kp.octave];
         const float* __restrict__ img = oc.G[kp.layer];
@@ -491,7 +495,7 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
         const float inv_hw = (float)(1.0 / hw);
         const float pori = (float)kp.pori;
         const float fix = (float)(4294967296.0 / ((hw + 2.0) * (hw + 2.0) * 361.0));
-        for (int b = lane; b < DESC_COPIES * 128; b += 32) hist[b] = 0u;
+        for (int b = lane; b < DESC_COPIES * DESC_WORDS; b += 32) hist[b] = 0u;
         __syncwarp();
         // |col*sa + row*ca| < 2.5 hw  and  |col*ca - row*sa| < 2.5 hw  (bins in (-1, 4)), widened
         const float lim = 2.5f * (float)hw + 0.5f;
@@ -548,7 +552,8 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
                 const float* c = img + (size_t)(rw + y) * pitch + (col + x);
                 const float dx = ldg(c + 1) - ldg(c - 1);
                 const float dy = ldg(c - pitch) - ldg(c + pitch);
-                const float mag = sqrtf(dx * dx + dy * dy);
+                const float g2 = dx * dx + dy * dy;
+                const float mag = g2 > 0.f ? g2 * rsqrtf(g2) : 0.f;
                 float ang = atan2f(dy, dx) - pori;  // in (-3pi, pi]
                 ang -= 6.283185307179586f * floorf(ang * (1.0f / 6.283185307179586f));
                 if (ang < 0.f) ang = 0.f;
@@ -559,21 +564,21 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
                 const float fbr = floorf(rb), fbc = floorf(cb), fbo = floorf(ob);
                 const int br = (int)fbr, bc = (int)fbc, bo = (int)fbo;
                 const float fr = rb - fbr, fc = cb - fbc, fo = ob - fbo;
-#pragma unroll
-                for (int a = 0; a <= 1; ++a) {
-                    const int ri = br + a;
-                    if (ri < 0 || ri >= 4) continue;
-                    const float vr = m * (a == 0 ? 1.0f - fr : fr);
-#pragma unroll
-                    for (int bq = 0; bq <= 1; ++bq) {
-                        const int ci = bc + bq;
-                        if (ci < 0 || ci >= 4) continue;
-                        const float vc = vr * (bq == 0 ? 1.0f - fc : fc);
-                        unsigned* cell = my_hist + (ri * 4 + ci) * 8;
-                        atomicAdd(cell + (bo & 7), __float2uint_rn(vc * (1.0f - fo)));
-                        atomicAdd(cell + ((bo + 1) & 7), __float2uint_rn(vc * fo));
-                    }
-                }
+                // trilinear spread (sift.cpp:541-571) into the 6x6 padded grid: rows / columns -1 and 4
+                // (dropped by the reference) land in the border, so no range tests are needed
+                unsigned* cell = my_hist + ((br + 1) * DESC_GRID + (bc + 1)) * 8;
+                const int o0 = bo & 7, o1 = (bo + 1) & 7;
+                const float w0 = 1.0f - fo;
+                const float v00 = m * (1.0f - fr) * (1.0f - fc), v01 = m * (1.0f - fr) * fc;
+                const float v10 = m * fr * (1.0f - fc), v11 = m * fr * fc;
+                atomicAdd(cell + o0, __float2uint_rn(v00 * w0));
+                atomicAdd(cell + o1, __float2uint_rn(v00 * fo));
+                atomicAdd(cell + 8 + o0, __float2uint_rn(v01 * w0));
+                atomicAdd(cell + 8 + o1, __float2uint_rn(v01 * fo));
+                atomicAdd(cell + DESC_GRID * 8 + o0, __float2uint_rn(v10 * w0));
+                atomicAdd(cell + DESC_GRID * 8 + o1, __float2uint_rn(v10 * fo));
+                atomicAdd(cell + DESC_GRID * 8 + 8 + o0, __float2uint_rn(v11 * w0));
+                atomicAdd(cell + DESC_GRID * 8 + 8 + o1, __float2uint_rn(v11 * fo));
             }
         }
         __syncwarp();
@@ -583,8 +588,10 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             unsigned long long t = 0;
+            // bin 4L+k = (row L/8, column (L/2)%4, orientation 4(L%2)+k) of the inner 4x4 cells
+            const int cellw = (((lane >> 3) + 1) * DESC_GRID + ((lane >> 1) & 3) + 1) * 8 + 4 * (lane & 1) + k;
 #pragma unroll
-            for (int cpy = 0; cpy < DESC_COPIES; ++cpy) t += hist[cpy * 128 + 4 * lane + k];
+            for (int cpy = 0; cpy < DESC_COPIES; ++cpy) t += hist[cpy * DESC_WORDS + cellw];
             hv[k] = (double)t;
             ss += hv[k] * hv[k];
         }
@@ -664,7 +671,7 @@ cudaError_t launch_sort_dedup(const KpCore* oriented, Counters* counters, const 
 cudaError_t launch_describe(const PyramidDesc* d_pyr, const KpCore* oriented, const int* final_order,
                             Counters* counters, uint8_t* records, uint8_t* desc, int cap_final,
                             const StageParams& sp, cudaStream_t s) {
-    k_describe<<<148 * 4, 256, 0, s>>>(d_pyr, oriented, final_order, counters, records, desc, cap_final, sp);
+    k_describe<<<148 * 4, DESC_WARPS * 32, 0, s>>>(d_pyr, oriented, final_order, counters, records, desc, cap_final, sp);
     return cudaGetLastError();
 }
 
