@@ -7,8 +7,8 @@
 // convert_to_grayscale + resize_inter_bilinear (image.cpp:8-24, 62-88) as the input stage.
 //
 // HBM-bound by design: one read of G[i-1], one write of G[i], one write of D[i-1] per level.
-#include "common.cuh"
-#include "kernels.h"
+#include "../sift_project_b200/csrc/common.cuh"
+#include "../sift_project_b200/csrc/kernels.h"
 
 namespace sb {
 
@@ -151,9 +151,7 @@ k_blur(const float* __restrict__ in, float* __restrict__ out, float* __restrict_
 // intermediate level must hold that level's edge value, not a blur of replicated input, so
 // border tiles re-replicate the edge after each intermediate level.
 // ------------------------------------------------------------------------------------------
-constexpr int CT = 512;  // threads per CTA of the fused kernels
-constexpr int CTW = 64;  // cascade tile width: 64 x 64 tiles need ~110 KB, so TWO CTAs share an SM and one
-                         // CTA's load / store phases overlap the other's arithmetic
+constexpr int CT = 512;  // threads per CTA of the fused kernel
 __host__ __device__ constexpr int ru4(int v) { return (v + 3) & ~3; }
 __host__ __device__ constexpr int ru2(int v) { return (v + 1) & ~1; }
 
@@ -163,13 +161,16 @@ struct CascadeGeom {
     static constexpr int HX2 = NL == 3 ? ru4(R3) : 0, HY2 = NL == 3 ? ru2(R3) : 0;  // halo kept around level 2
     static constexpr int HX1 = ru4(HX2 + R2), HY1 = ru2(HY2 + R2);                  // ... around level 1
     static constexpr int HX0 = ru4(HX1 + R1), HY0 = ru2(HY1 + R1);                  // ... around the input
-    static constexpr int W0 = CTW + 2 * HX0, H0 = TH + 2 * HY0;
-    static constexpr int W1 = CTW + 2 * HX1, H1 = TH + 2 * HY1;
-    static constexpr int W2 = CTW + 2 * HX2, H2 = TH + 2 * HY2;
-    static constexpr int A_FLOATS = W0 * H0;   // input, later level 2
-    static constexpr int T_FLOATS = W1 * H0;   // horizontal-pass scratch (largest: level 1)
-    static constexpr int B_FLOATS = W1 * H1;   // level 1
-    static constexpr size_t kSmem = (size_t)(A_FLOATS + T_FLOATS + B_FLOATS) * sizeof(float);
+    static constexpr int W0 = TW + 2 * HX0, H0 = TH + 2 * HY0;
+    static constexpr int W1 = TW + 2 * HX1, H1 = TH + 2 * HY1;
+    static constexpr int W2 = TW + 2 * HX2, H2 = TH + 2 * HY2;
+    static constexpr int H1P = (H1 + 7) & ~7, H2P = (H2 + 7) & ~7;   // vertical passes work on 8-row groups
+    // Two ping-pong buffers (input / level 1, then level 2 over the dead input; the next tile's
+    // input is prefetched into whichever is dead) and the horizontal-pass scratch.
+    static constexpr int cmax(int x, int y) { return x > y ? x : y; }
+    static constexpr int P_FLOATS = cmax(cmax(W0 * H0, W1 * H1P), W2 * H2P);
+    static constexpr int T_FLOATS = W1 * (H0 + 8);
+    static constexpr size_t kSmem = (size_t)(2 * P_FLOATS + T_FLOATS) * sizeof(float);
 };
 
 struct CascadeArgs {
@@ -179,11 +180,11 @@ struct CascadeArgs {
     float* dec;           // decimated copy of the LAST level (nullable)
     int w, h, pitch;
     int dec_w, dec_h, dec_pitch;
+    int tiles_x, tiles;
     BlurTaps taps[3];
 };
 
-// horizontal pass: out[r][4q..4q+3] (width OUT_W) from in (width IN_W); OFF = x offset of the output
-// region inside the input region (a multiple of 4)
+// horizontal pass, 4 outputs per item (used by the input kernel)
 template <int R, int IN_W, int OUT_W, int OFF>
 __device__ __forceinline__ void cascade_hpass(const float* __restrict__ in, float* __restrict__ out, int rows,
                                               const BlurTaps& taps) {
@@ -210,7 +211,39 @@ __device__ __forceinline__ void cascade_hpass(const float* __restrict__ in, floa
     }
 }
 
-// vertical pass: 4 columns x 4 rows per item, streaming down 4 + 2R scratch rows; emit(r, q, acc[4])
+// horizontal pass, 8 outputs per item: out[r][8q..8q+7] (width OUT_W) from in (width IN_W); OFF = x
+// offset of the output region inside the input region (a multiple of 4).  (8 + 2 ru4(R)) / 4 float4
+// loads feed 8 (2R+1)-tap outputs.
+template <int R, int IN_W, int OUT_W, int OFF>
+__device__ __forceinline__ void cascade_hpass8(const float* __restrict__ in, float* __restrict__ out, int rows,
+                                               const BlurTaps& taps) {
+    constexpr int HXR = ru4(R);
+    constexpr int Q = OUT_W / 8;
+    static_assert(OUT_W % 8 == 0, "8-wide horizontal pass");
+    for (int idx = threadIdx.x; idx < rows * Q; idx += CT) {
+        const int r = idx / Q, q = idx - r * Q;
+        const float4* src = reinterpret_cast<const float4*>(in + r * IN_W + OFF + 8 * q - HXR);
+        float v[8 + 2 * HXR];
+#pragma unroll
+        for (int k = 0; k < (8 + 2 * HXR) / 4; ++k) {
+            const float4 t = src[k];
+            v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+        }
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float acc = 0.f;
+#pragma unroll
+            for (int u = R; u >= 1; --u) acc = fmaf(taps.w[u], v[HXR + k - u] + v[HXR + k + u], acc);
+            o[k] = fmaf(taps.w[0], v[HXR + k], acc);
+        }
+        float4* dst = reinterpret_cast<float4*>(out + r * OUT_W + 8 * q);
+        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// vertical pass, 4 columns x 4 rows per item (used by the input kernel)
 template <int R, int W, typename Emit>
 __device__ __forceinline__ void cascade_vpass(const float* __restrict__ tmp, int out_rows, const BlurTaps& taps,
                                               Emit emit) {
@@ -239,10 +272,39 @@ __device__ __forceinline__ void cascade_vpass(const float* __restrict__ tmp, int
     }
 }
 
+// vertical pass, 2 columns x 8 rows per item, streaming down 8 + 2R scratch rows (float2 loads):
+// (8 + 2R) / 8 loads per output row instead of (4 + 2R) / 4.  emit(y, c, acc[8]) gets rows y..y+7 of
+// columns 2c, 2c+1.  The accumulation order per output (top row first) is the per-level kernel's.
+template <int R, int W, typename Emit>
+__device__ __forceinline__ void cascade_vpass8(const float* __restrict__ tmp, int row_groups, const BlurTaps& taps,
+                                               Emit emit) {
+    constexpr int C = W / 2;
+    for (int idx = threadIdx.x; idx < row_groups * C; idx += CT) {
+        const int g = idx / C, c = idx - g * C;
+        float2 acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 8 + 2 * R; ++r) {
+            const float2 t = *reinterpret_cast<const float2*>(tmp + (8 * g + r) * W + 2 * c);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int d = (r - k - R) < 0 ? (k + R - r) : (r - k - R);
+                if (d <= R) {
+                    const float wt = taps.w[d];
+                    acc[k].x = fmaf(wt, t.x, acc[k].x);
+                    acc[k].y = fmaf(wt, t.y, acc[k].y);
+                }
+            }
+        }
+        emit(8 * g, c, acc);
+    }
+}
+
 // re-replicate the image edge into the out-of-image part of a staged level (border tiles only)
-template <int W, int H>
-__device__ __forceinline__ void cascade_fix_edges(float* __restrict__ buf, int gx0, int gy0, int w, int h) {
-    for (int idx = threadIdx.x; idx < W * H; idx += CT) {
+template <int W>
+__device__ __forceinline__ void cascade_fix_edges(float* __restrict__ buf, int rows, int gx0, int gy0, int w, int h) {
+    for (int idx = threadIdx.x; idx < W * rows; idx += CT) {
         const int r = idx / W, c = idx - r * W;
         const int gx = gx0 + c, gy = gy0 + r;
         const int cx = min(max(gx, 0), w - 1), cy = min(max(gy, 0), h - 1);
@@ -250,132 +312,173 @@ __device__ __forceinline__ void cascade_fix_edges(float* __restrict__ buf, int g
     }
 }
 
+#ifdef SB_PHASE_TIMING
+__device__ unsigned long long g_phase[16];
+#define SB_PHASE(p)                                                            \
+    do {                                                                       \
+        if (threadIdx.x == 0) {                                                \
+            const long long now__ = clock64();                                 \
+            atomicAdd(&g_phase[p], (unsigned long long)(now__ - phase_t0__));  \
+            phase_t0__ = now__;                                                \
+        }                                                                      \
+    } while (0)
+#define SB_PHASE_INIT long long phase_t0__ = clock64();
+#else
+#define SB_PHASE(p)
+#define SB_PHASE_INIT
+#endif
+
 template <int R1, int R2, int R3>
-__global__ void __launch_bounds__(CT, 2) k_cascade(const CascadeArgs a) {
+__global__ void __launch_bounds__(CT, 1) k_cascade(const CascadeArgs a) {
     using G = CascadeGeom<R1, R2, R3>;
+    SB_PHASE_INIT
     extern __shared__ __align__(16) float smem[];
-    float* sA = smem;
-    float* sT = sA + G::A_FLOATS;
-    float* sB = sT + G::T_FLOATS;
+    float* bufP = smem;                      // input of the current tile
+    float* bufQ = smem + G::P_FLOATS;        // level 1
+    float* sT = smem + 2 * G::P_FLOATS;      // horizontal-pass scratch
     const int tid = threadIdx.x;
     const int w = a.w, h = a.h, pitch = a.pitch;
-    const int tx0 = blockIdx.x * CTW, ty0 = blockIdx.y * TH;
-    const int gx0 = tx0 - G::HX0, gy0 = ty0 - G::HY0;
-    const bool interior = gx0 >= 0 && gy0 >= 0 && (tx0 + CTW + G::HX0) <= w && (ty0 + TH + G::HY0) <= h;
 
-    // ---- stage the input tile (replicate padding == the reference's index clamping) ----
-    if (interior) {
+    auto tile_origin = [&](int t, int& tx0, int& ty0) {
+        const int ty = t / a.tiles_x;
+        tx0 = (t - ty * a.tiles_x) * TW;
+        ty0 = ty * TH;
+    };
+    auto is_interior = [&](int tx0, int ty0) {
+        return tx0 - G::HX0 >= 0 && ty0 - G::HY0 >= 0 && (tx0 + TW + G::HX0) <= w && (ty0 + TH + G::HY0) <= h;
+    };
+    // asynchronous copy of an interior tile's input (one commit group)
+    auto prefetch = [&](float* dst, int tx0, int ty0) {
         constexpr int V = G::W0 / 4;
+        const float* src = a.in + (size_t)(ty0 - G::HY0) * pitch + (tx0 - G::HX0);
         for (int idx = tid; idx < G::H0 * V; idx += CT) {
             const int r = idx / V, c4 = idx - r * V;
-            cp_async16(sA + r * G::W0 + 4 * c4, a.in + (size_t)(gy0 + r) * pitch + gx0 + 4 * c4);
+            cp_async16(dst + r * G::W0 + 4 * c4, src + (size_t)r * pitch + 4 * c4);
         }
-        cp_async_wait_all();
-    } else {
-        for (int idx = tid; idx < G::H0 * G::W0; idx += CT) {
-            const int r = idx / G::W0, c = idx - r * G::W0;
-            const int gy = min(max(gy0 + r, 0), h - 1), gx = min(max(gx0 + c, 0), w - 1);
-            sA[idx] = __ldg(a.in + (size_t)gy * pitch + gx);
-        }
-    }
-    __syncthreads();
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
 
-    // store helper: 4 rows x 4 columns of a level and of its DoG against `prev` (shared memory)
-    auto store_level = [&](float* gout, float* dout, const float* prev, int prev_w, int prev_ox, int prev_oy,
-                           int y, int q, const float4 (&acc)[4], bool decimate) {
-        const int gx = tx0 + 4 * q;
-        if (gx >= w) return;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int gy = ty0 + y + k;
-            if (gy >= h) break;
-            const float4 o = acc[k];
-            if (gout != nullptr) *reinterpret_cast<float4*>(gout + (size_t)gy * pitch + gx) = o;
-            const float4 c = *reinterpret_cast<const float4*>(prev + (prev_oy + y + k) * prev_w + prev_ox + 4 * q);
-            *reinterpret_cast<float4*>(dout + (size_t)gy * pitch + gx) =
-                make_float4(o.x - c.x, o.y - c.y, o.z - c.z, o.w - c.w);
-            if (decimate && a.dec != nullptr && !(gy & 1)) {
-                const int dy = gy >> 1, dx = gx >> 1;
-                if (dy < a.dec_h) {
-                    if (dx + 1 < a.dec_w)
-                        *reinterpret_cast<float2*>(a.dec + (size_t)dy * a.dec_pitch + dx) = make_float2(o.x, o.z);
-                    else if (dx < a.dec_w)
-                        a.dec[(size_t)dy * a.dec_pitch + dx] = o.x;
+    int t = blockIdx.x;
+    bool have_input = false;   // the current tile's input is already (being) copied into bufP
+    for (; t < a.tiles; t += gridDim.x) {
+        int tx0, ty0;
+        tile_origin(t, tx0, ty0);
+        const bool interior = is_interior(tx0, ty0);
+        // ---- stage the input tile (replicate padding == the reference's index clamping) ----
+        if (!have_input) {
+            if (interior) {
+                prefetch(bufP, tx0, ty0);
+            } else {
+                const int gx0 = tx0 - G::HX0, gy0 = ty0 - G::HY0;
+                for (int idx = tid; idx < G::H0 * G::W0; idx += CT) {
+                    const int r = idx / G::W0, c = idx - r * G::W0;
+                    const int gy = min(max(gy0 + r, 0), h - 1), gx = min(max(gx0 + c, 0), w - 1);
+                    bufP[idx] = __ldg(a.in + (size_t)gy * pitch + gx);
                 }
             }
         }
-    };
-
-    // ---- level 1: sA -> sT -> sB ----
-    cascade_hpass<R1, G::W0, G::W1, G::HX0 - G::HX1>(sA, sT, G::H0, a.taps[0]);
-    __syncthreads();
-    cascade_vpass<R1, G::W1>(sT + (G::HY0 - G::HY1 - R1) * G::W1, G::H1, a.taps[0],
-                             [&](int y, int q, const float4 (&acc)[4]) {
-#pragma unroll
-                                 for (int k = 0; k < 4; ++k)
-                                     *reinterpret_cast<float4*>(sB + (y + k) * G::W1 + 4 * q) = acc[k];
-                             });
-    __syncthreads();
-    // emit the centre of level 1 (+ DoG against the input centre)
-    for (int idx = tid; idx < (TH / 4) * (CTW / 4); idx += CT) {
-        const int g = idx / (CTW / 4), q = idx - g * (CTW / 4);
-        float4 acc[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            acc[k] = *reinterpret_cast<const float4*>(sB + (G::HY1 + 4 * g + k) * G::W1 + G::HX1 + 4 * q);
-        store_level(a.g[0], a.d[0], sA, G::W0, G::HX0, G::HY0, 4 * g, q, acc, false);
-    }
-    if (!interior) {
-        __syncthreads();
-        cascade_fix_edges<G::W1, G::H1>(sB, tx0 - G::HX1, ty0 - G::HY1, w, h);
-    }
-    __syncthreads();
-
-    if (G::NL == 3) {
-        // ---- level 2: sB -> sT -> sA (the input is dead by now) ----
-        cascade_hpass<R2, G::W1, G::W2, G::HX1 - G::HX2>(sB, sT, G::H1, a.taps[1]);
-        __syncthreads();
-        cascade_vpass<R2, G::W2>(sT + (G::HY1 - G::HY2 - R2) * G::W2, G::H2, a.taps[1],
-                                 [&](int y, int q, const float4 (&acc)[4]) {
-#pragma unroll
-                                     for (int k = 0; k < 4; ++k)
-                                         *reinterpret_cast<float4*>(sA + (y + k) * G::W2 + 4 * q) = acc[k];
-                                 });
-        __syncthreads();
-        for (int idx = tid; idx < (TH / 4) * (CTW / 4); idx += CT) {
-            const int g = idx / (CTW / 4), q = idx - g * (CTW / 4);
-            float4 acc[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                acc[k] = *reinterpret_cast<const float4*>(sA + (G::HY2 + 4 * g + k) * G::W2 + G::HX2 + 4 * q);
-            store_level(a.g[1], a.d[1], sB, G::W1, G::HX1, G::HY1, 4 * g, q, acc, false);
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads(); SB_PHASE(0);
+        have_input = false;
+        const int tn = t + gridDim.x;
+        int ntx0 = 0, nty0 = 0;
+        bool next_interior = false;
+        if (tn < a.tiles) {
+            tile_origin(tn, ntx0, nty0);
+            next_interior = is_interior(ntx0, nty0);
         }
+
+        // emit rows y..y+7 (level-region coordinates) of two columns of a level: G, DoG against
+        // the previous level (shared memory), and optionally the decimated copy
+        auto store_rows = [&](float* gout, float* dout, const float* prev, int prev_w, int prev_ox, int prev_oy,
+                              int hx, int hy, int y, int c, const float2 (&acc)[8], bool decimate) {
+            const int lx = 2 * c - hx;            // column inside the tile
+            if (lx < 0 || lx >= TW) return;
+            const int gx = tx0 + lx;
+            if (gx >= w) return;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int ly = y + k - hy;        // row inside the tile
+                const int gy = ty0 + ly;
+                if (ly < 0 || ly >= TH || gy >= h) continue;
+                const float2 o = acc[k];
+                if (gout != nullptr) *reinterpret_cast<float2*>(gout + (size_t)gy * pitch + gx) = o;
+                const float2 p = *reinterpret_cast<const float2*>(prev + (prev_oy + ly) * prev_w + prev_ox + lx);
+                *reinterpret_cast<float2*>(dout + (size_t)gy * pitch + gx) = make_float2(o.x - p.x, o.y - p.y);
+                if (decimate && a.dec != nullptr && !(gy & 1)) {
+                    const int dy = gy >> 1, dx = gx >> 1;
+                    if (dy < a.dec_h && dx < a.dec_w) a.dec[(size_t)dy * a.dec_pitch + dx] = o.x;
+                }
+            }
+        };
+
+        // ---- level 1: bufP -> sT -> bufQ (+ G1 / D0 of the tile centre straight from registers) ----
+        cascade_hpass8<R1, G::W0, G::W1, G::HX0 - G::HX1>(bufP, sT, G::H0, a.taps[0]);
+        __syncthreads(); SB_PHASE(1);
+        cascade_vpass8<R1, G::W1>(sT + (G::HY0 - G::HY1 - R1) * G::W1, G::H1P / 8, a.taps[0],
+                                  [&](int y, int c, const float2 (&acc)[8]) {
+#pragma unroll
+                                      for (int k = 0; k < 8; ++k)
+                                          *reinterpret_cast<float2*>(bufQ + (y + k) * G::W1 + 2 * c) = acc[k];
+                                      store_rows(a.g[0], a.d[0], bufP, G::W0, G::HX0, G::HY0, G::HX1, G::HY1, y, c, acc,
+                                                 false);
+                                  });
+        __syncthreads(); SB_PHASE(2);
         if (!interior) {
-            __syncthreads();
-            cascade_fix_edges<G::W2, G::H2>(sA, tx0 - G::HX2, ty0 - G::HY2, w, h);
+            cascade_fix_edges<G::W1>(bufQ, G::H1, tx0 - G::HX1, ty0 - G::HY1, w, h);
+            __syncthreads(); SB_PHASE(3);
         }
-        __syncthreads();
-        // ---- level 3: sA -> sT -> registers -> HBM ----
-        cascade_hpass<(R3 > 0 ? R3 : 1), G::W2, CTW, G::HX2>(sA, sT, G::H2, a.taps[2]);
-        __syncthreads();
-        cascade_vpass<(R3 > 0 ? R3 : 1), CTW>(sT + (G::HY2 - R3) * CTW, TH, a.taps[2],
-                                           [&](int y, int q, const float4 (&acc)[4]) {
-                                               store_level(a.g[2], a.d[2], sA, G::W2, G::HX2, G::HY2, y, q, acc, true);
-                                           });
-    } else {
-        // ---- two-level variant: level 2 is the last: sB -> sT -> registers -> HBM ----
-        cascade_hpass<R2, G::W1, CTW, G::HX1>(sB, sT, G::H1, a.taps[1]);
-        __syncthreads();
-        cascade_vpass<R2, CTW>(sT + (G::HY1 - R2) * CTW, TH, a.taps[1],
-                              [&](int y, int q, const float4 (&acc)[4]) {
-                                  store_level(a.g[1], a.d[1], sB, G::W1, G::HX1, G::HY1, y, q, acc, true);
-                              });
+
+        if (G::NL == 3) {
+            // ---- level 2: bufQ -> sT -> bufP (the input is dead by now) ----
+            cascade_hpass8<R2, G::W1, G::W2, G::HX1 - G::HX2>(bufQ, sT, G::H1, a.taps[1]);
+            __syncthreads(); SB_PHASE(4);
+            cascade_vpass8<R2, G::W2>(sT + (G::HY1 - G::HY2 - R2) * G::W2, G::H2P / 8, a.taps[1],
+                                      [&](int y, int c, const float2 (&acc)[8]) {
+#pragma unroll
+                                          for (int k = 0; k < 8; ++k)
+                                              *reinterpret_cast<float2*>(bufP + (y + k) * G::W2 + 2 * c) = acc[k];
+                                          store_rows(a.g[1], a.d[1], bufQ, G::W1, G::HX1, G::HY1, G::HX2, G::HY2, y, c,
+                                                     acc, false);
+                                      });
+            __syncthreads(); SB_PHASE(5);
+            if (!interior) {
+                cascade_fix_edges<G::W2>(bufP, G::H2, tx0 - G::HX2, ty0 - G::HY2, w, h);
+                __syncthreads(); SB_PHASE(6);
+            }
+            // level 1 is dead: the next tile's input streams into its buffer during level 3
+            if (next_interior) { prefetch(bufQ, ntx0, nty0); have_input = true; }
+            // ---- level 3: bufP -> sT -> registers -> HBM ----
+            cascade_hpass8<(R3 > 0 ? R3 : 1), G::W2, TW, G::HX2>(bufP, sT, G::H2, a.taps[2]);
+            __syncthreads(); SB_PHASE(7);
+            cascade_vpass8<(R3 > 0 ? R3 : 1), TW>(sT + (G::HY2 - R3) * TW, TH / 8, a.taps[2],
+                                                  [&](int y, int c, const float2 (&acc)[8]) {
+                                                      store_rows(a.g[2], a.d[2], bufP, G::W2, G::HX2, G::HY2, 0, 0, y, c,
+                                                                 acc, true);
+                                                  });
+            // roles swap: the prefetched input lives in bufQ
+            float* tmp = bufP; bufP = bufQ; bufQ = tmp;
+        } else {
+            // ---- two-level variant: the input is dead after level 1, prefetch into it; level 2 is
+            // the last: bufQ -> sT -> registers -> HBM ----
+            if (next_interior) { prefetch(bufP, ntx0, nty0); have_input = true; }
+            cascade_hpass8<R2, G::W1, TW, G::HX1>(bufQ, sT, G::H1, a.taps[1]);
+            __syncthreads(); SB_PHASE(8);
+            cascade_vpass8<R2, TW>(sT + (G::HY1 - R2) * TW, TH / 8, a.taps[1],
+                                   [&](int y, int c, const float2 (&acc)[8]) {
+                                       store_rows(a.g[1], a.d[1], bufQ, G::W1, G::HX1, G::HY1, 0, 0, y, c, acc, true);
+                                   });
+        }
+        __syncthreads(); SB_PHASE(9);   // sT / buffers are rewritten by the next tile
     }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
 template <int R1, int R2, int R3>
-cudaError_t launch_cascade_t(const CascadeArgs& a, cudaStream_t s) {
-    dim3 grid((a.w + CTW - 1) / CTW, (a.h + TH - 1) / TH);
+cudaError_t launch_cascade_t(CascadeArgs a, int sm_count, cudaStream_t s) {
+    a.tiles_x = (a.w + TW - 1) / TW;
+    a.tiles = a.tiles_x * ((a.h + TH - 1) / TH);
+    const int grid = a.tiles < sm_count ? a.tiles : sm_count;   // persistent: one CTA per SM
     k_cascade<R1, R2, R3><<<grid, CT, CascadeGeom<R1, R2, R3>::kSmem, s>>>(a);
     return cudaGetLastError();
 }
@@ -546,7 +649,7 @@ bool cascade_supported(const BlurTaps* taps) {
 
 // One octave: G[0] -> G[1..3], D[0..4], next base.  keep_all also stores G[4], G[5] (debug planes).
 cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, float* dec, int dec_w, int dec_h,
-                                int dec_pitch, bool keep_all, cudaStream_t s) {
+                                int dec_pitch, bool keep_all, int sm_count, cudaStream_t s) {
     CascadeArgs a;
     a.in = od.G[0];
     a.g[0] = od.G[1]; a.g[1] = od.G[2]; a.g[2] = od.G[3];
@@ -554,7 +657,7 @@ cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, floa
     a.dec = dec; a.dec_w = dec_w; a.dec_h = dec_h; a.dec_pitch = dec_pitch;
     a.w = od.w; a.h = od.h; a.pitch = od.pitch;
     a.taps[0] = taps[1]; a.taps[1] = taps[2]; a.taps[2] = taps[3];
-    cudaError_t e = launch_cascade_t<4, 5, 6>(a, s);
+    cudaError_t e = launch_cascade_t<4, 5, 6>(a, sm_count, s);
     if (e != cudaSuccess) return e;
     CascadeArgs b;
     b.in = od.G[3];
@@ -563,7 +666,7 @@ cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, floa
     b.dec = nullptr; b.dec_w = b.dec_h = b.dec_pitch = 0;
     b.w = od.w; b.h = od.h; b.pitch = od.pitch;
     b.taps[0] = taps[4]; b.taps[1] = taps[5]; b.taps[2] = taps[5];
-    return launch_cascade_t<8, 10, 0>(b, s);
+    return launch_cascade_t<8, 10, 0>(b, sm_count, s);
 }
 
 cudaError_t launch_prepare_u8(const uint8_t* src, int sw, int sh, int ch, float* dst, int dw, int dh,
