@@ -250,9 +250,26 @@ __device__ __forceinline__ void cascade_fix_edges(float* __restrict__ buf, int g
     }
 }
 
+#ifdef SB_PHASE_TIMING   // scratch/casc_prof.cu: per-phase cycle counters (thread 0 of every CTA)
+__device__ unsigned long long g_phase[16];
+#define SB_PHASE(p)                                                            \
+    do {                                                                       \
+        if (threadIdx.x == 0) {                                                \
+            const long long now__ = clock64();                                 \
+            atomicAdd(&g_phase[p], (unsigned long long)(now__ - phase_t0__));  \
+            phase_t0__ = now__;                                                \
+        }                                                                      \
+    } while (0)
+#define SB_PHASE_INIT long long phase_t0__ = clock64();
+#else
+#define SB_PHASE(p)
+#define SB_PHASE_INIT
+#endif
+
 template <int R1, int R2, int R3>
 __global__ void __launch_bounds__(CT, 2) k_cascade(const CascadeArgs a) {
     using G = CascadeGeom<R1, R2, R3>;
+    SB_PHASE_INIT
     extern __shared__ __align__(16) float smem[];
     float* sA = smem;
     float* sT = sA + G::A_FLOATS;
@@ -279,6 +296,7 @@ __global__ void __launch_bounds__(CT, 2) k_cascade(const CascadeArgs a) {
         }
     }
     __syncthreads();
+    SB_PHASE(0);
 
     // store helper: 4 rows x 4 columns of a level and of its DoG against `prev` (shared memory)
     auto store_level = [&](float* gout, float* dout, const float* prev, int prev_w, int prev_ox, int prev_oy,
@@ -309,6 +327,7 @@ __global__ void __launch_bounds__(CT, 2) k_cascade(const CascadeArgs a) {
     // ---- level 1: sA -> sT -> sB ----
     cascade_hpass<R1, G::W0, G::W1, G::HX0 - G::HX1>(sA, sT, G::H0, a.taps[0]);
     __syncthreads();
+    SB_PHASE(1);
     cascade_vpass<R1, G::W1>(sT + (G::HY0 - G::HY1 - R1) * G::W1, G::H1, a.taps[0],
                              [&](int y, int q, const float4 (&acc)[4]) {
 #pragma unroll
@@ -316,6 +335,7 @@ __global__ void __launch_bounds__(CT, 2) k_cascade(const CascadeArgs a) {
                                      *reinterpret_cast<float4*>(sB + (y + k) * G::W1 + 4 * q) = acc[k];
                              });
     __syncthreads();
+    SB_PHASE(2);
     // emit the centre of level 1 (+ DoG against the input centre)
     for (int idx = tid; idx < (TH / 4) * (CTW / 4); idx += CT) {
         const int g = idx / (CTW / 4), q = idx - g * (CTW / 4);
@@ -327,14 +347,17 @@ __global__ void __launch_bounds__(CT, 2) k_cascade(const CascadeArgs a) {
     }
     if (!interior) {
         __syncthreads();
+    SB_PHASE(3);
         cascade_fix_edges<G::W1, G::H1>(sB, tx0 - G::HX1, ty0 - G::HY1, w, h);
     }
     __syncthreads();
+    SB_PHASE(4);
 
     if (G::NL == 3) {
         // ---- level 2: sB -> sT -> sA (the input is dead by now) ----
         cascade_hpass<R2, G::W1, G::W2, G::HX1 - G::HX2>(sB, sT, G::H1, a.taps[1]);
         __syncthreads();
+    SB_PHASE(5);
         cascade_vpass<R2, G::W2>(sT + (G::HY1 - G::HY2 - R2) * G::W2, G::H2, a.taps[1],
                                  [&](int y, int q, const float4 (&acc)[4]) {
 #pragma unroll
@@ -342,6 +365,7 @@ __global__ void __launch_bounds__(CT, 2) k_cascade(const CascadeArgs a) {
                                          *reinterpret_cast<float4*>(sA + (y + k) * G::W2 + 4 * q) = acc[k];
                                  });
         __syncthreads();
+    SB_PHASE(6);
         for (int idx = tid; idx < (TH / 4) * (CTW / 4); idx += CT) {
             const int g = idx / (CTW / 4), q = idx - g * (CTW / 4);
             float4 acc[4];
@@ -352,12 +376,15 @@ __global__ void __launch_bounds__(CT, 2) k_cascade(const CascadeArgs a) {
         }
         if (!interior) {
             __syncthreads();
+    SB_PHASE(7);
             cascade_fix_edges<G::W2, G::H2>(sA, tx0 - G::HX2, ty0 - G::HY2, w, h);
         }
         __syncthreads();
+    SB_PHASE(8);
         // ---- level 3: sA -> sT -> registers -> HBM ----
         cascade_hpass<(R3 > 0 ? R3 : 1), G::W2, CTW, G::HX2>(sA, sT, G::H2, a.taps[2]);
         __syncthreads();
+    SB_PHASE(9);
         cascade_vpass<(R3 > 0 ? R3 : 1), CTW>(sT + (G::HY2 - R3) * CTW, TH, a.taps[2],
                                            [&](int y, int q, const float4 (&acc)[4]) {
                                                store_level(a.g[2], a.d[2], sA, G::W2, G::HX2, G::HY2, y, q, acc, true);
@@ -366,11 +393,13 @@ __global__ void __launch_bounds__(CT, 2) k_cascade(const CascadeArgs a) {
         // ---- two-level variant: level 2 is the last: sB -> sT -> registers -> HBM ----
         cascade_hpass<R2, G::W1, CTW, G::HX1>(sB, sT, G::H1, a.taps[1]);
         __syncthreads();
+    SB_PHASE(10);
         cascade_vpass<R2, CTW>(sT + (G::HY1 - R2) * CTW, TH, a.taps[1],
                               [&](int y, int q, const float4 (&acc)[4]) {
                                   store_level(a.g[1], a.d[1], sB, G::W1, G::HX1, G::HY1, y, q, acc, true);
                               });
     }
+    SB_PHASE(15);
 }
 
 template <int R1, int R2, int R3>
