@@ -53,7 +53,9 @@ struct Counters {
     int n_oriented;
     int n_final;
     int overflow;  // bit 0 extrema, bit 1 raw, bit 2 oriented
-    int pad[3];
+    int next_orient;    // work-stealing cursors of the warp-per-keypoint kernels
+    int next_describe;
+    int pad[1];
 };
 
 // Parameters of the per-keypoint stages, all FP64 like the reference's scalars.

@@ -220,7 +220,12 @@ k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, Kp
     const int n = min(counters->n_raw, sp.cap_raw);
     unsigned* hist = &s_hist[warp][0][0];
     unsigned* my_hist = s_hist[warp][lane & (ORI_COPIES - 1)];
-    for (int i = blockIdx.x * 8 + warp; i < n; i += gridDim.x * 8) {
+    // keypoints cost 4x more or less than one another: warps pull the next one from a shared cursor
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&counters->next_orient, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n) break;
         const KpCore kp = raw[i];
         const OctaveDesc& oc = pyr->oct[kp.octave];
         const float* __restrict__ img = oc.G[kp.layer];
@@ -471,7 +476,7 @@ constexpr int DESC_WORDS = DESC_GRID * DESC_GRID * 8;   // per histogram copy
 
 __global__ void __launch_bounds__(DESC_WARPS * 32)
 k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ oriented,
-           const int* __restrict__ final_order, const Counters* __restrict__ counters,
+           const int* __restrict__ final_order, Counters* __restrict__ counters,
            uint8_t* __restrict__ records, uint8_t* __restrict__ desc, int cap_final, const StageParams sp) {
     __shared__ unsigned s_hist[DESC_WARPS][DESC_COPIES][DESC_WORDS];
     const unsigned FULL = 0xffffffffu;
@@ -479,7 +484,11 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
     unsigned* hist = &s_hist[warp][0][0];
     unsigned* my_hist = s_hist[warp][lane & (DESC_COPIES - 1)];
     const int n = min(counters->n_final, cap_final);
-    for (int i = blockIdx.x * DESC_WARPS + warp; i < n; i += gridDim.x * DESC_WARPS) {
+    for (;;) {   // work stealing: the window area varies 4x between keypoints
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&counters->next_describe, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n) break;
         const KpCore kp = oriented[final_order[i]];
         const OctaveDesc& oc = pyr->oct[kp.octave];
         const float* __restrict__ img = oc.G[kp.layer];

@@ -427,6 +427,23 @@ k_input_u8(const uint8_t* __restrict__ src, int sw, int sh, float* __restrict__ 
     float* sA = smem;
     float* sT = smem + IN_W0 * IN_H0;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    const bool inside = tx0 - IN_R >= 0 && ty0 - IN_R >= 0 && tx0 + TW + IN_R <= w && ty0 + TH + IN_R <= h;
+    if (DOUBLED && inside) {
+        // interior tiles: one source pixel neighbourhood -> a 2x2 block of the up-sampled tile
+        // (p, (p+q)/2; (p+t)/2, ((p+q)/2+(t+u)/2)/2 -- the same exact quarter-integers)
+        const int sx0 = (tx0 - IN_R) >> 1, sy0 = (ty0 - IN_R) >> 1;   // tile origin is even
+        for (int idx = threadIdx.x; idx < (IN_W0 / 2) * (IN_H0 / 2); idx += CT) {
+            const int br = idx / (IN_W0 / 2), bc = idx - br * (IN_W0 / 2);
+            const int x0 = sx0 + bc, y0 = sy0 + br;
+            const int x1 = min(x0 + 1, sw - 1), y1 = min(y0 + 1, sh - 1);
+            const float p = __ldg(src + (size_t)y0 * sw + x0), q = __ldg(src + (size_t)y0 * sw + x1);
+            const float t = __ldg(src + (size_t)y1 * sw + x0), u = __ldg(src + (size_t)y1 * sw + x1);
+            const float top = p * 0.5f + q * 0.5f, bot = t * 0.5f + u * 0.5f;
+            *reinterpret_cast<float2*>(sA + (2 * br) * IN_W0 + 2 * bc) = make_float2(p, top);
+            *reinterpret_cast<float2*>(sA + (2 * br + 1) * IN_W0 + 2 * bc) =
+                make_float2(p * 0.5f + t * 0.5f, top * 0.5f + bot * 0.5f);
+        }
+    } else
     for (int idx = threadIdx.x; idx < IN_W0 * IN_H0; idx += CT) {
         const int r = idx / IN_W0, c = idx - r * IN_W0;
         const int X = min(max(tx0 - IN_R + c, 0), w - 1), Y = min(max(ty0 - IN_R + r, 0), h - 1);
