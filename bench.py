@@ -448,7 +448,7 @@ def main():
     ap.add_argument("--images", type=int, default=256, help="global batch (config: 256)")
     ap.add_argument("--width", type=int, default=W4K)
     ap.add_argument("--height", type=int, default=H4K)
-    ap.add_argument("--contexts", type=int, default=3, help="contexts (streams) in flight per GPU")
+    ap.add_argument("--contexts", type=int, default=4, help="contexts (streams) in flight per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

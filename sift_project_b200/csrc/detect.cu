@@ -652,7 +652,7 @@ cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int threshold, Can
 
 cudaError_t launch_refine(const PyramidDesc* d_pyr, const Cand* cands, KpCore* raw, Counters* counters,
                           const StageParams& sp, cudaStream_t s) {
-    k_refine<<<148 * 4, 128, 0, s>>>(d_pyr, cands, raw, counters, sp);
+    k_refine<<<148 * 16, 128, 0, s>>>(d_pyr, cands, raw, counters, sp);
     return cudaGetLastError();
 }
 
