@@ -152,6 +152,8 @@ k_blur(const float* __restrict__ in, float* __restrict__ out, float* __restrict_
 // border tiles re-replicate the edge after each intermediate level.
 // ------------------------------------------------------------------------------------------
 constexpr int CT = 512;  // threads per CTA of the fused kernels
+constexpr int CCT = 384; // threads per cascade CTA: the 64x64 tile's pass sizes (2304/528/1760/380/1216/256 items)
+                         // split into whole rounds of 384 far better than of 512
 constexpr int CTW = 64;  // cascade tile width: 64 x 64 tiles need ~110 KB, so TWO CTAs share an SM and one
                          // CTA's load / store phases overlap the other's arithmetic
 __host__ __device__ constexpr int ru4(int v) { return (v + 3) & ~3; }
@@ -184,12 +186,12 @@ struct CascadeArgs {
 
 // horizontal pass: out[r][4q..4q+3] (width OUT_W) from in (width IN_W); OFF = x offset of the output
 // region inside the input region (a multiple of 4)
-template <int R, int IN_W, int OUT_W, int OFF>
+template <int NTH, int R, int IN_W, int OUT_W, int OFF>
 __device__ __forceinline__ void cascade_hpass(const float* __restrict__ in, float* __restrict__ out, int rows,
                                               const BlurTaps& taps) {
     constexpr int HXR = ru4(R);
     constexpr int Q = OUT_W / 4;
-    for (int idx = threadIdx.x; idx < rows * Q; idx += CT) {
+    for (int idx = threadIdx.x; idx < rows * Q; idx += NTH) {
         const int r = idx / Q, q = idx - r * Q;
         const float4* src = reinterpret_cast<const float4*>(in + r * IN_W + OFF + 4 * q - HXR);
         float v[4 + 2 * HXR];
@@ -211,11 +213,11 @@ __device__ __forceinline__ void cascade_hpass(const float* __restrict__ in, floa
 }
 
 // vertical pass: 4 columns x 4 rows per item, streaming down 4 + 2R scratch rows; emit(r, q, acc[4])
-template <int R, int W, typename Emit>
+template <int NTH, int R, int W, typename Emit>
 __device__ __forceinline__ void cascade_vpass(const float* __restrict__ tmp, int out_rows, const BlurTaps& taps,
                                               Emit emit) {
     constexpr int Q = W / 4;
-    for (int idx = threadIdx.x; idx < (out_rows / 4) * Q; idx += CT) {
+    for (int idx = threadIdx.x; idx < (out_rows / 4) * Q; idx += NTH) {
         const int g = idx / Q, q = idx - g * Q;
         float4 acc[4];
 #pragma unroll
@@ -240,9 +242,9 @@ __device__ __forceinline__ void cascade_vpass(const float* __restrict__ tmp, int
 }
 
 // re-replicate the image edge into the out-of-image part of a staged level (border tiles only)
-template <int W, int H>
+template <int NTH, int W, int H>
 __device__ __forceinline__ void cascade_fix_edges(float* __restrict__ buf, int gx0, int gy0, int w, int h) {
-    for (int idx = threadIdx.x; idx < W * H; idx += CT) {
+    for (int idx = threadIdx.x; idx < W * H; idx += NTH) {
         const int r = idx / W, c = idx - r * W;
         const int gx = gx0 + c, gy = gy0 + r;
         const int cx = min(max(gx, 0), w - 1), cy = min(max(gy, 0), h - 1);
@@ -267,7 +269,7 @@ __device__ unsigned long long g_phase[16];
 #endif
 
 template <int R1, int R2, int R3>
-__global__ void __launch_bounds__(CT, 2) k_cascade(const CascadeArgs a) {
+__global__ void __launch_bounds__(CCT, 2) k_cascade(const CascadeArgs a) {
     using G = CascadeGeom<R1, R2, R3>;
     SB_PHASE_INIT
     extern __shared__ __align__(16) float smem[];
@@ -283,13 +285,13 @@ __global__ void __launch_bounds__(CT, 2) k_cascade(const CascadeArgs a) {
     // ---- stage the input tile (replicate padding == the reference's index clamping) ----
     if (interior) {
         constexpr int V = G::W0 / 4;
-        for (int idx = tid; idx < G::H0 * V; idx += CT) {
+        for (int idx = tid; idx < G::H0 * V; idx += CCT) {
             const int r = idx / V, c4 = idx - r * V;
             cp_async16(sA + r * G::W0 + 4 * c4, a.in + (size_t)(gy0 + r) * pitch + gx0 + 4 * c4);
         }
         cp_async_wait_all();
     } else {
-        for (int idx = tid; idx < G::H0 * G::W0; idx += CT) {
+        for (int idx = tid; idx < G::H0 * G::W0; idx += CCT) {
             const int r = idx / G::W0, c = idx - r * G::W0;
             const int gy = min(max(gy0 + r, 0), h - 1), gx = min(max(gx0 + c, 0), w - 1);
             sA[idx] = __ldg(a.in + (size_t)gy * pitch + gx);
@@ -325,10 +327,10 @@ __global__ void __launch_bounds__(CT, 2) k_cascade(const CascadeArgs a) {
     };
 
     // ---- level 1: sA -> sT -> sB ----
-    cascade_hpass<R1, G::W0, G::W1, G::HX0 - G::HX1>(sA, sT, G::H0, a.taps[0]);
+    cascade_hpass<CCT, R1, G::W0, G::W1, G::HX0 - G::HX1>(sA, sT, G::H0, a.taps[0]);
     __syncthreads();
     SB_PHASE(1);
-    cascade_vpass<R1, G::W1>(sT + (G::HY0 - G::HY1 - R1) * G::W1, G::H1, a.taps[0],
+    cascade_vpass<CCT, R1, G::W1>(sT + (G::HY0 - G::HY1 - R1) * G::W1, G::H1, a.taps[0],
                              [&](int y, int q, const float4 (&acc)[4]) {
 #pragma unroll
                                  for (int k = 0; k < 4; ++k)
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(CT, 2) k_cascade(const CascadeArgs a) {
     __syncthreads();
     SB_PHASE(2);
     // emit the centre of level 1 (+ DoG against the input centre)
-    for (int idx = tid; idx < (TH / 4) * (CTW / 4); idx += CT) {
+    for (int idx = tid; idx < (TH / 4) * (CTW / 4); idx += CCT) {
         const int g = idx / (CTW / 4), q = idx - g * (CTW / 4);
         float4 acc[4];
 #pragma unroll
@@ -345,20 +347,20 @@ __global__ void __launch_bounds__(CT, 2) k_cascade(const CascadeArgs a) {
             acc[k] = *reinterpret_cast<const float4*>(sB + (G::HY1 + 4 * g + k) * G::W1 + G::HX1 + 4 * q);
         store_level(a.g[0], a.d[0], sA, G::W0, G::HX0, G::HY0, 4 * g, q, acc, false);
     }
+    // interior tiles go straight on: the next pass only reads what the emission reads
     if (!interior) {
         __syncthreads();
-    SB_PHASE(3);
-        cascade_fix_edges<G::W1, G::H1>(sB, tx0 - G::HX1, ty0 - G::HY1, w, h);
+        cascade_fix_edges<CCT, G::W1, G::H1>(sB, tx0 - G::HX1, ty0 - G::HY1, w, h);
+        __syncthreads();
     }
-    __syncthreads();
     SB_PHASE(4);
 
     if (G::NL == 3) {
         // ---- level 2: sB -> sT -> sA (the input is dead by now) ----
-        cascade_hpass<R2, G::W1, G::W2, G::HX1 - G::HX2>(sB, sT, G::H1, a.taps[1]);
+        cascade_hpass<CCT, R2, G::W1, G::W2, G::HX1 - G::HX2>(sB, sT, G::H1, a.taps[1]);
         __syncthreads();
     SB_PHASE(5);
-        cascade_vpass<R2, G::W2>(sT + (G::HY1 - G::HY2 - R2) * G::W2, G::H2, a.taps[1],
+        cascade_vpass<CCT, R2, G::W2>(sT + (G::HY1 - G::HY2 - R2) * G::W2, G::H2, a.taps[1],
                                  [&](int y, int q, const float4 (&acc)[4]) {
 #pragma unroll
                                      for (int k = 0; k < 4; ++k)
@@ -366,7 +368,7 @@ __global__ void __launch_bounds__(CT, 2) k_cascade(const CascadeArgs a) {
                                  });
         __syncthreads();
     SB_PHASE(6);
-        for (int idx = tid; idx < (TH / 4) * (CTW / 4); idx += CT) {
+        for (int idx = tid; idx < (TH / 4) * (CTW / 4); idx += CCT) {
             const int g = idx / (CTW / 4), q = idx - g * (CTW / 4);
             float4 acc[4];
 #pragma unroll
@@ -376,25 +378,24 @@ __global__ void __launch_bounds__(CT, 2) k_cascade(const CascadeArgs a) {
         }
         if (!interior) {
             __syncthreads();
-    SB_PHASE(7);
-            cascade_fix_edges<G::W2, G::H2>(sA, tx0 - G::HX2, ty0 - G::HY2, w, h);
+            cascade_fix_edges<CCT, G::W2, G::H2>(sA, tx0 - G::HX2, ty0 - G::HY2, w, h);
+            __syncthreads();
         }
-        __syncthreads();
     SB_PHASE(8);
         // ---- level 3: sA -> sT -> registers -> HBM ----
-        cascade_hpass<(R3 > 0 ? R3 : 1), G::W2, CTW, G::HX2>(sA, sT, G::H2, a.taps[2]);
+        cascade_hpass<CCT, (R3 > 0 ? R3 : 1), G::W2, CTW, G::HX2>(sA, sT, G::H2, a.taps[2]);
         __syncthreads();
     SB_PHASE(9);
-        cascade_vpass<(R3 > 0 ? R3 : 1), CTW>(sT + (G::HY2 - R3) * CTW, TH, a.taps[2],
+        cascade_vpass<CCT, (R3 > 0 ? R3 : 1), CTW>(sT + (G::HY2 - R3) * CTW, TH, a.taps[2],
                                            [&](int y, int q, const float4 (&acc)[4]) {
                                                store_level(a.g[2], a.d[2], sA, G::W2, G::HX2, G::HY2, y, q, acc, true);
                                            });
     } else {
         // ---- two-level variant: level 2 is the last: sB -> sT -> registers -> HBM ----
-        cascade_hpass<R2, G::W1, CTW, G::HX1>(sB, sT, G::H1, a.taps[1]);
+        cascade_hpass<CCT, R2, G::W1, CTW, G::HX1>(sB, sT, G::H1, a.taps[1]);
         __syncthreads();
     SB_PHASE(10);
-        cascade_vpass<R2, CTW>(sT + (G::HY1 - R2) * CTW, TH, a.taps[1],
+        cascade_vpass<CCT, R2, CTW>(sT + (G::HY1 - R2) * CTW, TH, a.taps[1],
                               [&](int y, int q, const float4 (&acc)[4]) {
                                   store_level(a.g[1], a.d[1], sB, G::W1, G::HX1, G::HY1, y, q, acc, true);
                               });
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(CT, 2) k_cascade(const CascadeArgs a) {
 template <int R1, int R2, int R3>
 cudaError_t launch_cascade_t(const CascadeArgs& a, cudaStream_t s) {
     dim3 grid((a.w + CTW - 1) / CTW, (a.h + TH - 1) / TH);
-    k_cascade<R1, R2, R3><<<grid, CT, CascadeGeom<R1, R2, R3>::kSmem, s>>>(a);
+    k_cascade<R1, R2, R3><<<grid, CCT, CascadeGeom<R1, R2, R3>::kSmem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -462,9 +463,9 @@ k_input_u8(const uint8_t* __restrict__ src, int sw, int sh, float* __restrict__ 
         sA[idx] = v;
     }
     __syncthreads();
-    cascade_hpass<IN_R, IN_W0, TW, IN_R>(sA, sT, IN_H0, taps);
+    cascade_hpass<CT, IN_R, IN_W0, TW, IN_R>(sA, sT, IN_H0, taps);
     __syncthreads();
-    cascade_vpass<IN_R, TW>(sT, TH, taps, [&](int y, int q, const float4 (&acc)[4]) {
+    cascade_vpass<CT, IN_R, TW>(sT, TH, taps, [&](int y, int q, const float4 (&acc)[4]) {
         const int gx = tx0 + 4 * q;
         if (gx >= w) return;
 #pragma unroll
