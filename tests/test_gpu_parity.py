@@ -360,3 +360,92 @@ def test_fused_octave_cascade_equals_per_level_kernels(ctx):
                 assert np.array_equal(x, y), (h, w, o, k, float(np.abs(x - y).max()))
         assert got.tobytes() == ref.tobytes(), (h, w)
     ctx.debug_options()
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json configs at full size.  Known answers of the REAL reference (SURVEY.md section 4,
+# measured with oracle/_ref on the same generator-D images): they pin the GPU path at sizes the CPU
+# oracle needs minutes for.
+# ------------------------------------------------------------------------------------------
+KNOWN = {  # (height, width, seed) -> (octaves, extrema, raw, oriented, final)
+    (1080, 1920, 1234): (9, 39448, 5776, 7259, 7240),
+    (2160, 3840, 1234): (10, 157361, 21887, 27555, 27536),
+}
+
+
+@pytest.mark.parametrize("shape", sorted(KNOWN))
+def test_full_size_stage_counts_match_reference_known_answers(shape):
+    h, w, seed = shape
+    octs, n_ext, n_raw, n_ori, n_fin = KNOWN[shape]
+    img = O.synth_image(h, w, seed=seed)
+    with S.SiftContext(w, h) as c:
+        k = c.detect(img)
+        st = c.stats()
+    REPORT[f"known_{w}x{h}"] = dict(stats=st, reference=dict(extrema=n_ext, raw=n_raw, oriented=n_ori, final=n_fin))
+    assert st["octaves"] == octs
+    for got, want in ((st["extrema"], n_ext), (st["raw_keypoints"], n_raw), (st["oriented_keypoints"], n_ori),
+                      (len(k), n_fin)):
+        assert abs(got - want) <= 0.005 * want, (got, want)   # 99.5 % set agreement implies this
+    # the reference's output order and de-duplication
+    key = np.stack([k["x"], k["y"], -k["size"], k["pori"], -k["octave"].astype(float)], 1)
+    assert np.array_equal(np.lexsort(key.T[::-1]), np.arange(len(k)))
+
+
+def test_config2_1080p_four_octaves_vs_oracle():
+    """Config 2: 1920x1080, 4 octaves x 5 scales.  The reference derives the octave count, so the
+    oracle is its result filtered to octave < 4 (octave o never depends on octaves > o)."""
+    img = O.synth_image(1080, 1920, seed=1234)
+    with S.SiftContext(1920, 1080) as c:
+        got = c.detect(img, max_octaves=4)
+    run = O.Run(O.best(), img, keep_pyramid=False)
+    want = run.keypoints(2)
+    want = want[want["octave"] < 4]
+    rec, prec, gi, wi = P.recall_precision(got, want)
+    rep = P.descriptor_report(got, want, gi, wi)
+    REPORT["config2_1080p_4oct"] = dict(n_gpu=len(got), n_ref=len(want), recall=rec, precision=prec, desc=rep)
+    assert rec >= 0.995 and prec >= 0.995
+    assert rep["frac_le1"] >= 0.99
+
+
+def test_config4_8k_properties():
+    """Config 4 (7680x4320): too large for the CPU oracle in a test; size-independent properties."""
+    import torch
+    sys_path_bench = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(sys_path_bench, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    img = bench.synth_image_gpu(4320, 7680, 1234, torch.device("cuda", 0))
+    torch.cuda.synchronize()
+    with S.SiftContext(7680, 4320) as c:
+        c.detect_enqueue(img, 7680, 4320)
+        n = c.detect_finish()
+        out = np.zeros(n, dtype=S.KP_DTYPE)
+        assert c.result_copy(out) == n
+        st = c.stats()
+        c.detect_enqueue(img, 7680, 4320)
+        out2 = np.zeros(n, dtype=S.KP_DTYPE)
+        assert c.detect_finish() == n and c.result_copy(out2) == n
+    REPORT["config4_8k"] = dict(stats=st)
+    assert st["octaves"] == 11 and st["base_width"] == 15360
+    assert 60000 < n < 200000                      # ~4 k keypoints per input megapixel
+    assert out.tobytes() == out2.tobytes()          # bit-reproducible
+    key = np.stack([out["x"], out["y"], -out["size"], out["pori"], -out["octave"].astype(float)], 1)
+    assert np.array_equal(np.lexsort(key.T[::-1]), np.arange(n))
+    assert out["x"].min() >= 0 and out["x"].max() < 7680 and out["y"].max() < 4320
+    assert set(np.unique(out["layer"])) <= {1, 2, 3}
+    assert (out["desc"].astype(np.float64) ** 2).sum(1).min() > 0   # no empty descriptors
+
+
+def test_match_self_is_identity(ctx):
+    """match(A, A): every row's nearest neighbour is itself at distance 0 (any size, both kernels)."""
+    import torch
+    a = O.synth_descriptors(5000, seed=77)
+    ta = torch.from_numpy(a).cuda()
+    idx = torch.empty(5000, dtype=torch.int32, device="cuda")
+    d1, d2 = torch.empty_like(idx), torch.empty_like(idx)
+    torch.cuda.synchronize()
+    ctx.match_enqueue(ta, 5000, ta, 5000, idx, d1, d2)
+    ctx.sync()
+    assert np.array_equal(idx.cpu().numpy(), np.arange(5000))
+    assert int(d1.max()) == 0 and int(d2.min()) > 0
