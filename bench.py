@@ -200,7 +200,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def cpu_baseline_sample(img_u8_host):
@@ -432,14 +432,120 @@ def run_b200(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "stages_ms": stages, "stage_launches": stage_launches, "match": match,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     for c in ctxs:
         c.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def run_collection(args):
+    """BASELINE.json config 5: `--sets` descriptor sets x `--per-set` descriptors, all-pairs matching
+    partitioned over the ranks by image pair, after ONE NCCL all-gather of the u8 descriptor blocks.
+    Timed region (CUDA events + barrier, max over ranks): all-gather + every pair's top-2 search."""
+    import torch
+    import torch.distributed as dist
+    import sift_project_b200 as S
+    from sift_project_b200 import collection as Cn
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    n_sets, per = args.sets, args.per_set
+
+    def synth_desc(n, seed):
+        g = torch.Generator(device=dev); g.manual_seed(seed)
+        hh = torch.randn((n, 128), generator=g, device=dev).abs()
+        hh = hh / hh.norm(dim=1, keepdim=True)
+        hh = hh.clamp(max=0.2)
+        hh = hh / hh.norm(dim=1, keepdim=True)
+        return torch.floor(512.0 * hh).clamp(max=255).to(torch.uint8).contiguous()
+
+    local_sets = {i: synth_desc(per, 1234 + i) for i in range(n_sets) if Cn.owner_of(i, world) == rank}
+    ctx = S.SiftContext(64, 64, device=local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    main_s = torch.cuda.current_stream()
+    pairs = Cn.partition_pairs([per] * n_sets, world)[rank]
+    idx = torch.empty((len(pairs), per), dtype=torch.int32, device=dev)
+    d1, d2 = torch.empty_like(idx), torch.empty_like(idx)
+    torch.cuda.synchronize()
+
+    def one_pass():
+        descs, _ = Cn.all_gather_descriptors(local_sets, n_sets, device=dev)   # NCCL, torch's stream
+        e = torch.cuda.Event(); e.record(main_s); stream.wait_event(e)
+        for k, (i, j) in enumerate(pairs):
+            ctx.match_enqueue(descs[i], per, descs[j], per, idx[k], d1[k], d2[k])
+        e2 = torch.cuda.Event(); e2.record(stream); main_s.wait_event(e2)
+
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        one_pass()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(device_ids=[local])
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(main_s)
+    for _ in range(args.steps):
+        one_pass()
+    t1.record(main_s)
+    torch.cuda.synchronize()
+    ms = torch.tensor([t0.elapsed_time(t1) / args.steps], dtype=torch.float64, device=dev)
+    matches = ((16 * d1.long() * d1.long()) < (9 * d2.long() * d2.long())).sum().to(torch.float64).reshape(1)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(matches, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        n_pairs = n_sets * (n_sets - 1) // 2
+        flop = 2.0 * n_pairs * per * per * 128
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        tpeak = (peaks.get("bf16_tflops_sustained") or 1400.0) * world
+        tf = flop / (float(ms.item()) * 1e-3) / 1e12
+        emit(({
+            "metric": "collection all-pairs match (top-2 + ratio test)", "value": tf, "unit": "TFLOP/s-equivalent",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms.item()),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"{n_sets} sets x {per} descriptors, {n_pairs} unordered pairs, "
+                                   f"all-gather of {n_sets * per * 128 / 1e9:.2f} GB + tile-partitioned matching",
+                       "pairs_on_rank0": len(pairs)},
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained x n_gpus"},
+            "matches": float(matches.item())}))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout: libraries that chat on fd 1 (NCCL's version banner,
+    torchrun notices) are routed to stderr; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -450,8 +556,14 @@ def main():
     ap.add_argument("--height", type=int, default=H4K)
     ap.add_argument("--contexts", type=int, default=4, help="contexts (streams) in flight per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="detect", choices=["detect", "collection"],
+                    help="detect = the headline metric; collection = config 5 (all-pairs matching over N GPUs)")
+    ap.add_argument("--sets", type=int, default=512)
+    ap.add_argument("--per-set", type=int, default=20000)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "collection":
+        run_collection(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_b200(args)
