@@ -49,6 +49,7 @@ struct __align__(1024) SmemLayout {
     uint8_t b[STAGES][B_BYTES];
     int cprime[EPI_WARPS][SLICE];    // per-warp staging of the per-column constants
     int merge[EPI_WARPS / 4][BM][4]; // column slices 1.. -> slice 0 hand-over
+    int2 exch[2][EPI_WARPS / 4][BM]; // per-tile exchange of (best, second) between the slices of a row
     unsigned long long full_b[STAGES], empty_b[STAGES];
     unsigned long long a_full[2], a_empty[2];
     unsigned long long tmem_full[2], tmem_empty[2];
@@ -288,6 +289,7 @@ k_match_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             const int t1 = (int)min((long long)n_tiles, t0 + (r_end - seg));
             const int part = (int)blockIdx.x - sc.cta_of((long long)m_tile * n_tiles);
             int best = INT_MAX, second = INT_MAX, bj = 0;
+            int bound = INT_MAX;   // upper bound of the row's second-best key over all column slices
             int2 cnext = __ldg(reinterpret_cast<const int2*>(cprime_b + (size_t)t0 * BN + slice * SLICE) + lane);
             for (int t = t0; t < t1; ++t) {
                 __syncwarp();
@@ -297,7 +299,7 @@ k_match_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                 // Pre-filter on the raw dot product: key_j = c'_j - 512 dot_j >= (nmin << 8) - 512 dot_j, so
                 // key_j < second  =>  dot_j > ((nmin << 8) - second) / 512 =: theta (floor keeps it safe).
                 const long long nmin8 = (long long)__ldg(half_min + 2 * t + (slice >> 1)) << 8;
-                int theta = (int)max((nmin8 - (long long)second) >> 9, -1ll);
+                int theta = (int)max((nmin8 - (long long)bound) >> 9, -1ll);
                 const int best_in = best;
                 __syncwarp();
                 mbar_wait(&S.tmem_full[acc], acc_phase);
@@ -340,7 +342,8 @@ k_match_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                                 const int nb_ = min(best, lo);
                                 second = min3(max(best, lo), second, hi);
                                 best = nb_;
-                                theta = (int)max((nmin8 - (long long)second) >> 9, -1ll);
+                                bound = min(bound, second);
+                                theta = (int)max((nmin8 - (long long)bound) >> 9, -1ll);
                             }
                         }
                     }
@@ -350,6 +353,24 @@ k_match_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                 // earlier column wins a tie), so a later equal distance must not look "smaller".
                 if (best != best_in) bj = t * BN + (best & 255);
                 best &= ~255; second &= ~255;
+                // The four column slices of a row each see a quarter of the columns; what matters for
+                // skipping is the row's second best over ALL of them.  Exchange (best, second) once
+                // per tile (double-buffered, one named barrier per TMEM-lane quarter) and take the
+                // second smallest of the eight values as the bound for the next tile.
+                {
+                    S.exch[t & 1][slice][row] = make_int2(best, second);
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + quarter) : "memory");
+                    int g1 = INT_MAX, g2 = INT_MAX;
+#pragma unroll
+                    for (int o = 0; o < EPI_WARPS / 4; ++o) {
+                        const int2 e = S.exch[t & 1][o][row];
+                        // (g1, g2) <- two smallest of {g1, g2, e.x, e.y}, e.x <= e.y
+                        const int n1 = min(g1, e.x);
+                        g2 = min3(max(g1, e.x), g2, e.y);
+                        g1 = n1;
+                    }
+                    bound = g2 & ~255;
+                }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
