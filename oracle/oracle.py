@@ -47,6 +47,18 @@ def synth_descriptors(n, seed=1234):
     return np.minimum(np.floor(512.0 * h), 255).astype(np.uint8)
 
 
+class Params(C.Structure):
+    """OracleParams / RefParams: the tunable arguments of sift.hh:65-71."""
+    _fields_ = [("double_image_size", C.c_int32), ("init_sigma", C.c_double), ("intervals", C.c_int32),
+                ("contrast_threshold", C.c_double), ("eigen_ratio", C.c_double), ("peak_ratio", C.c_double),
+                ("ori_sigma_factor", C.c_double), ("desc_scale_factor", C.c_double)]
+
+    def __init__(self, double_image_size=True, init_sigma=1.6, intervals=3, contrast_threshold=0.04,
+                 eigen_ratio=10.0, peak_ratio=0.8, ori_sigma_factor=1.5, desc_scale_factor=3.0):
+        super().__init__(int(bool(double_image_size)), init_sigma, intervals, contrast_threshold, eigen_ratio,
+                         peak_ratio, ori_sigma_factor, desc_scale_factor)
+
+
 class _Lib:
     def __init__(self, path, prefix):
         if not os.path.exists(path):
@@ -55,6 +67,7 @@ class _Lib:
         self.p = prefix
         f = self._f
         f("run_create", C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int])
+        f("run_create_ex", C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Params), C.c_int])
         f("run_destroy", None, [C.c_void_p])
         f("run_octaves", C.c_int, [C.c_void_p])
         f("run_sigmas", C.c_int, [C.c_void_p, C.c_void_p, C.c_int])
@@ -75,8 +88,9 @@ class _Lib:
 class Run:
     """All stage outputs of one detect call on the CPU (FP64)."""
 
-    def __init__(self, lib, image, double_image_size=True, keep_pyramid=True):
+    def __init__(self, lib, image, double_image_size=True, keep_pyramid=True, params=None):
         self._l = lib
+        self.params = params
         img = np.ascontiguousarray(image, dtype=np.float64)
         if img.ndim == 2:
             h, w = img.shape
@@ -84,7 +98,10 @@ class Run:
         else:
             h, w, c = img.shape
         self.h, self.w, self.c = h, w, c
-        self._h = lib.run_create(img.ctypes.data, w, h, c, int(double_image_size), int(keep_pyramid))
+        if params is None:
+            self._h = lib.run_create(img.ctypes.data, w, h, c, int(double_image_size), int(keep_pyramid))
+        else:
+            self._h = lib.run_create_ex(img.ctypes.data, w, h, c, C.byref(params), int(keep_pyramid))
         self.keep = keep_pyramid
 
     def close(self):

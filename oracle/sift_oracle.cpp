@@ -18,9 +18,6 @@ namespace {
 
 constexpr double kPi = 3.14159265358979323846;  // M_PI
 constexpr double kTwoPi = 6.283185307179586;    // M_PI2, sift.hh:5
-constexpr int kIntervals = 3;                   // sift.hh:67
-constexpr int kLayers = kIntervals + 3;         // sift.cpp:144
-constexpr int kDogs = kIntervals + 2;           // sift.cpp:212
 constexpr int kMaxSteps = 5;                    // sift.hh:7
 constexpr int kBins = 36;                       // sift.hh:69
 
@@ -183,6 +180,9 @@ bool kp_same(const OracleKeypoint& a, const OracleKeypoint& b) {
 }  // namespace
 
 struct OracleRun {
+    OracleParams p;          // sift.hh:65-71 arguments
+    int layers() const { return p.intervals + 3; }  // sift.cpp:144
+    int dogs() const { return p.intervals + 2; }    // sift.cpp:212
     std::vector<double> sigmas;
     std::vector<Octave> G, D;
     std::vector<Cand> extrema;
@@ -193,7 +193,8 @@ namespace {
 
 // sift.cpp:113-155 + :181-225
 void build_pyramid(OracleRun& r, const double* px, int w, int h, int c, bool doubled) {
-    const double sigma0 = 1.6;
+    const double sigma0 = r.p.init_sigma;
+    const int kIntervals = r.p.intervals, kLayers = r.layers(), kDogs = r.dogs();
     Plane base = to_gray(px, w, h, c);
     if (doubled) base = upsample2(base);
     base = blur(base, std::sqrt(sigma0 * sigma0 - 1));  // sift.cpp:124 (always "-1")
@@ -231,7 +232,8 @@ void build_pyramid(OracleRun& r, const double* px, int w, int h, int c, bool dou
 
 // sift.cpp:264-319 -- x outer, y, z inner; the threshold lands in an int parameter.
 void scan_extrema(OracleRun& r) {
-    const int thr = (int)std::floor(0.5 * 0.04 / (double)kIntervals * 255.0);
+    const int kIntervals = r.p.intervals, kDogs = r.dogs();
+    const int thr = (int)std::floor(0.5 * r.p.contrast_threshold / (double)kIntervals * 255.0);
     for (int o = 0; o < (int)r.D.size(); ++o) {
         const Octave& D = r.D[o];
         for (int x = 1; x < D[0].w - 1; ++x)
@@ -245,7 +247,8 @@ void scan_extrema(OracleRun& r) {
 
 // sift.cpp:330-436
 void refine(OracleRun& r) {
-    const double contrast = 0.04, ratio = 10.0, sigma0 = 1.6;
+    const double contrast = r.p.contrast_threshold, ratio = r.p.eigen_ratio, sigma0 = r.p.init_sigma;
+    const int kIntervals = r.p.intervals, kDogs = r.dogs();
     for (const Cand& e : r.extrema) {
         const Octave& D = r.D[e.o];
         const int W = D[0].w, H = D[0].h;
@@ -292,7 +295,7 @@ void refine(OracleRun& r) {
 
 // sift.cpp:447-533
 void orient(OracleRun& r, bool doubled) {
-    const double peak_ratio = 0.8, factor = 1.5;
+    const double peak_ratio = r.p.peak_ratio, factor = r.p.ori_sigma_factor;
     for (const OracleKeypoint& kp : r.raw) {
         double inv = 1.0 / std::pow(2, kp.octave);
         int x = (int)std::round(kp.x * inv), y = (int)std::round(kp.y * inv);
@@ -337,7 +340,7 @@ void orient(OracleRun& r, bool doubled) {
 
 // sift.cpp:541-603 + :610-682
 void describe(OracleRun& r, bool doubled) {
-    const double scale_factor = 3.0;
+    const double scale_factor = r.p.desc_scale_factor;
     for (OracleKeypoint& kp : r.final_kps) {
         const Plane& I = r.G[kp.octave][kp.layer];
         double inv = doubled ? (1.0 / std::pow(2, kp.octave - 1)) : (1.0 / std::pow(2, kp.octave));
@@ -407,10 +410,24 @@ void describe(OracleRun& r, bool doubled) {
 
 extern "C" {
 
+void oracle_default_params(OracleParams* p) {
+    p->double_image_size = 1; p->init_sigma = 1.6; p->intervals = 3; p->contrast_threshold = 0.04;
+    p->eigen_ratio = 10.0; p->peak_ratio = 0.8; p->ori_sigma_factor = 1.5; p->desc_scale_factor = 3.0;
+}
+
 OracleRun* oracle_run_create(const double* pixels, int w, int h, int c, int double_image_size,
                              int keep_pyramid) {
+    OracleParams p;
+    oracle_default_params(&p);
+    p.double_image_size = double_image_size;
+    return oracle_run_create_ex(pixels, w, h, c, &p, keep_pyramid);
+}
+
+OracleRun* oracle_run_create_ex(const double* pixels, int w, int h, int c, const OracleParams* params,
+                                int keep_pyramid) {
     OracleRun* r = new OracleRun();
-    bool doubled = double_image_size != 0;
+    r->p = *params;
+    bool doubled = params->double_image_size != 0;
     build_pyramid(*r, pixels, w, h, c, doubled);
     scan_extrema(*r);
     refine(*r);

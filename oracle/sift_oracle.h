@@ -26,6 +26,16 @@ typedef struct OracleKeypoint {
     uint8_t desc[128];
 } OracleKeypoint;
 
+/* The tunable arguments of detect_keypoints_and_descriptors (sift.hh:65-71); window_size and
+ * num_bins stay at the reference defaults (3, 36). */
+typedef struct OracleParams {
+    int32_t double_image_size;
+    double init_sigma;
+    int32_t intervals;
+    double contrast_threshold, eigen_ratio, peak_ratio, ori_sigma_factor, desc_scale_factor;
+} OracleParams;
+void oracle_default_params(OracleParams* p);
+
 typedef struct OracleRun OracleRun;
 
 /* Runs every stage of detect_keypoints_and_descriptors (sift.cpp:712-776) with the reference's
@@ -33,6 +43,8 @@ typedef struct OracleRun OracleRun;
  * pixels: interleaved row-major doubles 0..255, c = 1 or 3 (image_io.cpp:81-83). */
 OracleRun* oracle_run_create(const double* pixels, int w, int h, int c, int double_image_size,
                              int keep_pyramid);
+OracleRun* oracle_run_create_ex(const double* pixels, int w, int h, int c, const OracleParams* params,
+                                int keep_pyramid);
 void oracle_run_destroy(OracleRun* r);
 int oracle_run_octaves(const OracleRun* r);
 int oracle_run_sigmas(const OracleRun* r, double* out, int cap);

@@ -140,3 +140,28 @@ def test_copy_free_reference_build_is_bit_identical_to_as_shipped():
     a, b = O.Run(O.ref(asshipped=True), img), O.Run(O.ref(), img)
     same_kps(a.keypoints(2), b.keypoints(2), True)
     assert np.array_equal(a.extrema(), b.extrema())
+
+
+PARAM_SETS = [
+    dict(init_sigma=1.3, contrast_threshold=0.03, eigen_ratio=6.0, peak_ratio=0.7, ori_sigma_factor=1.2,
+         desc_scale_factor=2.5),
+    dict(double_image_size=False, init_sigma=2.0, contrast_threshold=0.08, eigen_ratio=15.0, peak_ratio=0.9,
+         ori_sigma_factor=1.8, desc_scale_factor=3.5),
+    dict(intervals=2, contrast_threshold=0.05),
+    dict(intervals=4, init_sigma=1.4, peak_ratio=0.75),
+]
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not prebuilt")
+@pytest.mark.parametrize("kw", PARAM_SETS)
+def test_port_equals_real_reference_with_non_default_arguments(kw):
+    """Every tunable argument of sift.hh:65-71 (intervals included) through both implementations."""
+    img = O.synth_image(150, 200, seed=21)
+    r = O.Run(O.ref(), img, params=O.Params(**kw))
+    p = O.Run(O.port(), img, params=O.Params(**kw))
+    assert r.octaves == p.octaves
+    assert np.array_equal(r.sigmas(), p.sigmas())
+    assert np.array_equal(r.extrema(), p.extrema())
+    for s in (0, 1, 2):
+        same_kps(r.keypoints(s), p.keypoints(s), s == 2)
+    assert len(r.keypoints(2)) > 10
