@@ -449,3 +449,25 @@ def test_match_self_is_identity(ctx):
     ctx.sync()
     assert np.array_equal(idx.cpu().numpy(), np.arange(5000))
     assert int(d1.max()) == 0 and int(d2.min()) > 0
+
+
+@pytest.mark.parametrize("kw", [
+    dict(init_sigma=1.3, contrast_threshold=0.03, eigen_ratio=6.0, peak_ratio=0.7, ori_sigma_factor=1.2,
+         desc_scale_factor=2.5),
+    dict(double_image_size=False, init_sigma=2.0, contrast_threshold=0.08, eigen_ratio=15.0, peak_ratio=0.9,
+         ori_sigma_factor=1.8, desc_scale_factor=3.5),
+    dict(contrast_threshold=0.02, eigen_ratio=20.0, peak_ratio=0.6),
+])
+def test_non_default_arguments_vs_oracle(ctx, kw):
+    """The tunable arguments of sift.hh:65-71 (other sigmas take the per-level blur kernels instead
+    of the fused cascade)."""
+    img = O.synth_image(300, 400, seed=31)
+    got = ctx.detect(img, **kw)
+    want = O.Run(O.best(), img, params=O.Params(**kw), keep_pyramid=False).keypoints(2)
+    rec, prec, gi, wi = P.recall_precision(got, want)
+    rep = P.descriptor_report(got, want, gi, wi)
+    REPORT["params_" + "_".join(f"{k}={v}" for k, v in sorted(kw.items()))[:60]] = dict(
+        n_gpu=len(got), n_ref=len(want), recall=rec, precision=prec, desc=rep)
+    assert len(want) > 30
+    assert rec >= 0.99 and prec >= 0.99
+    assert rep["frac_le1"] >= 0.98
