@@ -44,9 +44,11 @@ typedef struct sift_b200_keypoint {
 } sift_b200_keypoint;
 
 /* The arguments of detect_keypoints_and_descriptors (sift.hh:65-71), same meaning and defaults.
- * This build implements intervals == 3, window_size == 3, num_bins == 36 (the reference's
- * defaults; get_pixel_cube is hard-wired to 3x3x3 there too, sift.cpp:35-37); other values
- * return SIFT_B200_E_UNSUPPORTED.  max_octaves is an extension: 0 = derive as the reference does
+ * This build implements intervals in 2..5, window_size == 3, num_bins == 36 (window and bins are
+ * the reference's defaults; get_pixel_cube is hard-wired to 3x3x3 there too, sift.cpp:35-37); other
+ * values, and init_sigma / intervals combinations whose blur radius exceeds 16, return
+ * SIFT_B200_E_UNSUPPORTED.  The fused per-octave kernels serve the default sigmas; other settings
+ * run one blur kernel per level (same arithmetic).  max_octaves is an extension: 0 = derive as the reference does
  * (sift.cpp:132-137), n > 0 = stop after n octaves. */
 typedef struct sift_b200_params {
     int32_t double_image_size;  /* 1 */

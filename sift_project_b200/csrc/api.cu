@@ -53,6 +53,7 @@ struct sift_b200_ctx {
     bool detect_pending = false;
     bool have_result = false;
     int base_w = 0, base_h = 0;
+    int layers = kLayers, dogs = kDogs;   // of the last detect (intervals + 3, intervals + 2)
     sift_b200_stats stats{};
     bool keep_planes = false;    // also store G[4], G[5] (debug plane access)
     bool force_unfused = false;  // per-level kernels instead of the fused octave cascade
@@ -131,7 +132,7 @@ bool is_device_ptr(const void* p) {
 size_t plane_floats(int w, int h) { return (size_t)round_up(w, 32) * h; }
 
 // Carve the arena into planes for a base image of bw x bh with `octaves` octaves.
-void layout_pyramid(sift_b200_ctx* c, int bw, int bh, int octaves) {
+void layout_pyramid(sift_b200_ctx* c, int bw, int bh, int octaves, int layers, int dogs) {
     float* p = c->arena;
     c->pyr.octaves = octaves;
     int w = bw, h = bh;
@@ -139,27 +140,27 @@ void layout_pyramid(sift_b200_ctx* c, int bw, int bh, int octaves) {
         OctaveDesc& od = c->pyr.oct[o];
         od.w = w; od.h = h; od.pitch = round_up(w, 32);
         const size_t n = plane_floats(w, h);
-        for (int i = 0; i < kLayers; ++i) { od.G[i] = p; p += n; }
-        for (int i = 0; i < kDogs; ++i) { od.D[i] = p; p += n; }
+        for (int i = 0; i < kMaxLayers; ++i) { od.G[i] = i < layers ? p : nullptr; if (i < layers) p += n; }
+        for (int i = 0; i < kMaxDogs; ++i) { od.D[i] = i < dogs ? p : nullptr; if (i < dogs) p += n; }
         w /= 2; h /= 2;
     }
 }
 
-size_t arena_need(int bw, int bh) {
+size_t arena_need(int bw, int bh, int planes = kLayers + kDogs) {
     size_t total = 0;
     int w = bw, h = bh;
     for (int o = 0; o < kMaxOctaves && w >= 1 && h >= 1; ++o) {
-        total += (size_t)(kLayers + kDogs) * plane_floats(w, h);
+        total += (size_t)planes * plane_floats(w, h);
         w /= 2; h /= 2;
     }
     return total + 64;
 }
 
 int check_params(sift_b200_ctx* c, const sift_b200_params& p) {
-    if (p.intervals != 3 || p.window_size != 3 || p.num_bins != 36.0)
+    if (p.intervals < 2 || p.intervals > kMaxIntervals || p.window_size != 3 || p.num_bins != 36.0)
         return fail(c, SIFT_B200_E_UNSUPPORTED,
-                    "this build implements intervals=3, window_size=3, num_bins=36 (got %d, %d, %g)",
-                    p.intervals, p.window_size, p.num_bins);
+                    "this build implements intervals in 2..%d, window_size=3, num_bins=36 (got %d, %d, %g)",
+                    kMaxIntervals, p.intervals, p.window_size, p.num_bins);
     if (!(p.init_sigma > 1.0) || p.init_sigma > 3.0)
         return fail(c, SIFT_B200_E_UNSUPPORTED, "init_sigma must be in (1, 3] (got %g)", p.init_sigma);
     if (p.max_octaves < 0) return fail(c, SIFT_B200_E_INVALID, "max_octaves < 0");
@@ -233,14 +234,16 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
                     c->max_w, c->max_h);
     const int doubled = p.double_image_size ? 1 : 0;
     const int bw = doubled ? 2 * width : width, bh = doubled ? 2 * height : height;
-    if (arena_need(bw, bh) > c->arena_floats)
+    const int layers = p.intervals + 3, dogs = p.intervals + 2;
+    if (arena_need(bw, bh, layers + dogs) > c->arena_floats)
         return fail(c, SIFT_B200_E_TOO_LARGE, "image %dx%d exceeds the context's workspace", width, height);
     int octaves = octave_count(bw, bh);
     if (p.max_octaves > 0) octaves = std::min(octaves, p.max_octaves);
     octaves = std::min(octaves, kMaxOctaves);
     if (octaves < 0) octaves = 0;
     // resize_inter_nearest throws below 2x2 (image.cpp:42-44); octave_count never gets there
-    layout_pyramid(c, bw, bh, octaves);
+    layout_pyramid(c, bw, bh, octaves, layers, dogs);
+    c->layers = layers; c->dogs = dogs;
     c->base_w = bw; c->base_h = bh;
     cudaStream_t s = c->stream;
     CU(c, cudaMemcpyAsync(c->d_pyr, &c->pyr, sizeof(PyramidDesc), cudaMemcpyHostToDevice, s));
@@ -249,6 +252,7 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     StageParams& sp = c->sp;
     sp.doubled = doubled;
     sp.intervals = p.intervals;
+    sp.dogs = dogs;
     sp.dog_threshold = (int)floor(0.5 * p.contrast_threshold / p.intervals * 255.0);  // sift.cpp:305-307
     sp.init_sigma = p.init_sigma;
     sp.contrast_threshold = p.contrast_threshold;
@@ -275,20 +279,22 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     }
 
     // Scale-space sigmas, compute_gaussian_kernels sift.cpp:143-155.
-    double sig[kLayers];
+    double sig[kMaxLayers];
     const double k = pow(2.0, 1.0 / p.intervals);
     sig[0] = p.init_sigma;
-    for (int i = 1; i < kLayers; ++i) sig[i] = pow(k, i - 1) * p.init_sigma * sqrt(k * k - 1);
-    BlurTaps taps[kLayers];
+    for (int i = 1; i < layers; ++i) sig[i] = pow(k, i - 1) * p.init_sigma * sqrt(k * k - 1);
+    BlurTaps taps[kMaxLayers];
     taps[0] = make_taps(sqrt(p.init_sigma * p.init_sigma - 1.0));  // sift.cpp:124: "-1" in both modes
-    for (int i = 1; i < kLayers; ++i) taps[i] = make_taps(sig[i]);
-    for (int i = 0; i < kLayers; ++i)
-        if (taps[i].radius > 12) return fail(c, SIFT_B200_E_UNSUPPORTED, "blur radius %d > 12", taps[i].radius);
+    for (int i = 1; i < layers; ++i) taps[i] = make_taps(sig[i]);
+    for (int i = 0; i < layers; ++i)
+        if (taps[i].radius > kMaxRadius)
+            return fail(c, SIFT_B200_E_UNSUPPORTED, "blur radius %d > %d (init_sigma / intervals combination)",
+                        taps[i].radius, kMaxRadius);
 
     // Stage 0: gray (+2x) into a scratch plane (octave 0's G[5] slot, dead until the cascade
     // reaches it), then the initial blur into G[0].
     OctaveDesc& o0 = c->pyr.oct[0];
-    float* scratch = o0.G[5];
+    float* scratch = o0.G[layers - 1];
     if (sizeof(T) == 1 && input_fused_supported(channels, taps[0]) && !c->force_unfused) {
         CU(c, launch_input_u8((const uint8_t*)d_pixels, width, height, o0.G[0], bw, bh, o0.pitch, doubled, taps[0], s));
         prof_mark(c, SIFT_B200_STAGE_INPUT, 1);
@@ -303,7 +309,7 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     prof_mark(c, SIFT_B200_STAGE_INPUT, 2);
     }
 
-    const bool fused = cascade_supported(taps) && !c->force_unfused;
+    const bool fused = p.intervals == 3 && cascade_supported(taps) && !c->force_unfused;
     for (int o = 0; o < octaves; ++o) {
         OctaveDesc& od = c->pyr.oct[o];
         if (fused) {
@@ -316,19 +322,19 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
             CU(c, launch_octave_fused(od, taps, dec, dw, dh, dp, c->keep_planes, s));
             prof_mark(c, SIFT_B200_STAGE_PYRAMID, 2);
         } else {
-        for (int i = 1; i < kLayers; ++i) {
+        for (int i = 1; i < layers; ++i) {
             float* dec = nullptr;
             int dw = 0, dh = 0, dp = 0;
-            if (i == kLayers - 3 && o + 1 < octaves) {  // next base = G[3] decimated, sift.cpp:195-196
+            if (i == layers - 3 && o + 1 < octaves) {  // next base = G[layers-3] decimated, sift.cpp:195-196
                 OctaveDesc& nx = c->pyr.oct[o + 1];
                 dec = nx.G[0]; dw = nx.w; dh = nx.h; dp = nx.pitch;
             }
             CU(c, launch_blur(od.G[i - 1], od.G[i], od.D[i - 1], dec, od.w, od.h, od.pitch, dw, dh, dp, taps[i], s));
         }
-        prof_mark(c, SIFT_B200_STAGE_PYRAMID, kLayers - 1);
+        prof_mark(c, SIFT_B200_STAGE_PYRAMID, layers - 1);
         }
         if (od.w >= 3 && od.h >= 3) {
-            CU(c, launch_extrema(od, o, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, s));
+            CU(c, launch_extrema(od, o, dogs, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, s));
             prof_mark(c, SIFT_B200_STAGE_EXTREMA, 1);
         }
     }
@@ -461,7 +467,7 @@ int sift_b200_create(int device, int max_width, int max_height, sift_b200_ctx** 
     CRT(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CRT(pyramid_init());
     CRT(match_init());
-    c->arena_floats = arena_need(2 * max_width, 2 * max_height);
+    c->arena_floats = arena_need(2 * max_width, 2 * max_height, kMaxLayers + kMaxDogs);
     CRT(cudaMalloc(&c->arena, c->arena_floats * sizeof(float)));
     c->input_bytes = (size_t)max_width * max_height * 3 * sizeof(float);
     CRT(cudaMalloc(&c->d_input, c->input_bytes));
@@ -716,8 +722,8 @@ int sift_b200_debug_plane(sift_b200_ctx* c, int kind, int octave, int layer, flo
     if (!c || !host_out || octave < 0 || octave >= c->pyr.octaves) return SIFT_B200_E_INVALID;
     const OctaveDesc& od = c->pyr.oct[octave];
     const float* src = nullptr;
-    if (kind == SIFT_B200_PLANE_GAUSSIAN && layer >= 0 && layer < kLayers) src = od.G[layer];
-    if (kind == SIFT_B200_PLANE_DOG && layer >= 0 && layer < kDogs) src = od.D[layer];
+    if (kind == SIFT_B200_PLANE_GAUSSIAN && layer >= 0 && layer < c->layers) src = od.G[layer];
+    if (kind == SIFT_B200_PLANE_DOG && layer >= 0 && layer < c->dogs) src = od.D[layer];
     if (!src) return fail(c, SIFT_B200_E_INVALID, "bad plane kind/layer");
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->stream));

@@ -6,8 +6,11 @@
 
 namespace sb {
 
-constexpr int kLayers = 6;      // Gaussian images per octave (intervals + 3, sift.cpp:144)
-constexpr int kDogs = 5;        // DoG images per octave (intervals + 2, sift.cpp:212)
+constexpr int kLayers = 6;      // Gaussian images per octave at the default intervals = 3 (intervals + 3, sift.cpp:144)
+constexpr int kDogs = 5;        // DoG images per octave at the default intervals (intervals + 2, sift.cpp:212)
+constexpr int kMaxIntervals = 5;
+constexpr int kMaxLayers = kMaxIntervals + 3;
+constexpr int kMaxDogs = kMaxIntervals + 2;
 constexpr int kMaxOctaves = 16;
 constexpr int kMaxRadius = 16;  // largest blur half-width this build instantiates
 constexpr int kOriBins = 36;    // sift.hh:69
@@ -20,8 +23,8 @@ constexpr double kUnfix = 1.0 / 4294967296.0;
 // (pitch is a multiple of 32 floats = 128 B so that rows are 16-byte aligned for vector loads).
 struct OctaveDesc {
     int w, h, pitch;
-    float* G[kLayers];  // G[0] is the octave base (sift.cpp:165)
-    float* D[kDogs];    // D[i] = G[i+1] - G[i] (sift.cpp:217)
+    float* G[kMaxLayers];  // G[0] is the octave base (sift.cpp:165); intervals + 3 are in use
+    float* D[kMaxDogs];    // D[i] = G[i+1] - G[i] (sift.cpp:217); intervals + 2 are in use
 };
 
 struct PyramidDesc {
@@ -62,6 +65,7 @@ struct Counters {
 struct StageParams {
     int doubled;
     int intervals;
+    int dogs;                 // intervals + 2
     int dog_threshold;        // floor(0.5*ct/intervals*255) squeezed into an int (sift.cpp:266,305)
     double init_sigma;
     double contrast_threshold;

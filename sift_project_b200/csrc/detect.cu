@@ -69,7 +69,7 @@ __device__ __noinline__ void extrema_emit(unsigned m, bool hit, int lane, int x,
 
 // EX_ROWS = output rows per warp: 32 on large octaves (2 halo rows per 32), 8 on small ones, where the
 // grid would otherwise not fill the GPU and a warp's serial walk down 34 rows is pure latency
-template <int EX_ROWS>
+template <int EX_ROWS, int ND>   // ND = DoG planes per octave (intervals + 2); planes 1 .. ND-2 are tested
 __global__ void __launch_bounds__(256, 4)
 k_extrema(const OctaveDesc oct, int octave, float thr, Cand* __restrict__ cands, int cap,
           Counters* __restrict__ counters) {
@@ -83,21 +83,21 @@ k_extrema(const OctaveDesc oct, int octave, float thr, Cand* __restrict__ cands,
     const bool lane_out = lane >= 1 && lane <= 30 && x <= w - 2;
 
     // 3 rotating window rows per plane: min / max over x-1..x+1, and the centre of planes 1..3
-    float hmin[kDogs][3], hmax[kDogs][3], ctr[3][3];
-    float raw[3][kDogs];  // rows loaded two iterations ahead of their use (bytes in flight hide HBM latency)
+    float hmin[ND][3], hmax[ND][3], ctr[ND - 2][3];
+    float raw[3][ND];  // rows loaded two iterations ahead of their use (bytes in flight hide HBM latency)
     auto fetch = [&](int y, int rs) {
         const int yc = min(y, h - 1);
 #pragma unroll
-        for (int z = 0; z < kDogs; ++z) raw[rs][z] = ldg(oct.D[z] + (size_t)yc * pitch + xc);
+        for (int z = 0; z < ND; ++z) raw[rs][z] = ldg(oct.D[z] + (size_t)yc * pitch + xc);
     };
     auto absorb = [&](int slot, int rs) {
 #pragma unroll
-        for (int z = 0; z < kDogs; ++z) {
+        for (int z = 0; z < ND; ++z) {
             const float v = raw[rs][z];
             const float l = __shfl_up_sync(FULL, v, 1), r = __shfl_down_sync(FULL, v, 1);
             hmin[z][slot] = fmin3(v, l, r);
             hmax[z][slot] = fmax3(v, l, r);
-            if (z >= 1 && z <= 3) ctr[z - 1][slot] = v;
+            if (z >= 1 && z <= ND - 2) ctr[z - 1][slot] = v;
         }
     };
     fetch(ys - 1, 0); fetch(ys, 1); fetch(ys + 1, 2);
@@ -113,14 +113,14 @@ k_extrema(const OctaveDesc oct, int octave, float thr, Cand* __restrict__ cands,
             const int mid = (kj + 1) % 3;
             absorb((kj + 2) % 3, (kj + 2) % 3);   // row y + 1 (fetched two iterations ago)
             fetch(y + 3, (kj + 1) % 3);           // in flight while this and the next row are tested
-            float vmin[kDogs], vmax[kDogs];
+            float vmin[ND], vmax[ND];
 #pragma unroll
-            for (int z = 0; z < kDogs; ++z) {
+            for (int z = 0; z < ND; ++z) {
                 vmin[z] = fmin3(hmin[z][0], hmin[z][1], hmin[z][2]);
                 vmax[z] = fmax3(hmax[z][0], hmax[z][1], hmax[z][2]);
             }
 #pragma unroll
-            for (int z = 1; z <= 3; ++z) {
+            for (int z = 1; z <= ND - 2; ++z) {
                 const float cv = ctr[z - 1][mid];
                 const float mx = fmax3(vmax[z - 1], vmax[z], vmax[z + 1]);
                 const float mn = fmin3(vmin[z - 1], vmin[z], vmin[z + 1]);
@@ -206,7 +206,7 @@ k_refine(const PyramidDesc* __restrict__ pyr, const Cand* __restrict__ cands, Kp
             layer += (int)round(f.off[0]);
             x += (int)round(f.off[1]);
             y += (int)round(f.off[2]);
-            if (x < 1 || x >= oc.w - 1 || y < 1 || y >= oc.h - 1 || layer < 1 || layer >= kDogs - 1) break;
+            if (x < 1 || x >= oc.w - 1 || y < 1 || y >= oc.h - 1 || layer < 1 || layer >= sp.dogs - 1) break;
         }
         if (!keep) continue;
         const double s = (double)(1 << e.o);  // pow(2, octave)
@@ -664,16 +664,21 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
 
 }  // namespace
 
-cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int threshold, Cand* cands, int cap,
+cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int threshold, Cand* cands, int cap,
                            Counters* counters, cudaStream_t s) {
     if (oct.w < 3 || oct.h < 3) return cudaSuccess;
-    if ((long long)oct.w * oct.h >= (16ll << 20)) {
-        dim3 grid((oct.w - 2 + 29) / 30, (oct.h - 2 + 8 * 32 - 1) / (8 * 32));
-        k_extrema<32><<<grid, 256, 0, s>>>(oct, octave, (float)threshold, cands, cap, counters);
-    } else {
-        dim3 grid((oct.w - 2 + 29) / 30, (oct.h - 2 + 8 * 8 - 1) / (8 * 8));
-        k_extrema<8><<<grid, 256, 0, s>>>(oct, octave, (float)threshold, cands, cap, counters);
+    const bool big = (long long)oct.w * oct.h >= (16ll << 20);
+    dim3 grid((oct.w - 2 + 29) / 30, (oct.h - 2 + 8 * (big ? 32 : 8) - 1) / (8 * (big ? 32 : 8)));
+#define SB_EX(ND)                                                                                            \
+    case ND:                                                                                                 \
+        if (big) k_extrema<32, ND><<<grid, 256, 0, s>>>(oct, octave, (float)threshold, cands, cap, counters); \
+        else k_extrema<8, ND><<<grid, 256, 0, s>>>(oct, octave, (float)threshold, cands, cap, counters);      \
+        break;
+    switch (dogs) {
+        SB_EX(4) SB_EX(5) SB_EX(6) SB_EX(7)
+        default: return cudaErrorInvalidValue;
     }
+#undef SB_EX
     return cudaGetLastError();
 }
 

@@ -573,7 +573,7 @@ cudaError_t pyramid_init() {
                                   (int)CascadeGeom<8, 10, 0>::kSmem)) != cudaSuccess) return e;
 #define SB_INIT(R) if ((e = init_blur_r<R>()) != cudaSuccess) return e;
     SB_INIT(1) SB_INIT(2) SB_INIT(3) SB_INIT(4) SB_INIT(5) SB_INIT(6) SB_INIT(7) SB_INIT(8)
-    SB_INIT(9) SB_INIT(10) SB_INIT(11) SB_INIT(12)
+    SB_INIT(9) SB_INIT(10) SB_INIT(11) SB_INIT(12) SB_INIT(13) SB_INIT(14) SB_INIT(15) SB_INIT(16)
 #undef SB_INIT
     return cudaSuccess;
 }
@@ -584,7 +584,7 @@ cudaError_t launch_blur(const float* in, float* out, float* dog, float* dec, int
     case R: return launch_blur_r<R>(in, out, dog, dec, w, h, pitch, dec_w, dec_h, dec_pitch, taps, s);
     switch (taps.radius) {
         SB_CASE(1) SB_CASE(2) SB_CASE(3) SB_CASE(4) SB_CASE(5) SB_CASE(6) SB_CASE(7) SB_CASE(8)
-        SB_CASE(9) SB_CASE(10) SB_CASE(11) SB_CASE(12)
+        SB_CASE(9) SB_CASE(10) SB_CASE(11) SB_CASE(12) SB_CASE(13) SB_CASE(14) SB_CASE(15) SB_CASE(16)
         default: return cudaErrorInvalidValue;
     }
 #undef SB_CASE

@@ -237,9 +237,11 @@ def test_flat_image_has_no_keypoints(ctx):
 
 def test_error_behaviour(ctx):
     img = O.synth_image(64, 64, seed=1)
-    with pytest.raises(S.SiftError) as e:
-        ctx.detect(img, intervals=4)
-    assert e.value.code == 5
+    for bad in (dict(intervals=1), dict(intervals=6), dict(window_size=5), dict(num_bins=18),
+                dict(intervals=2, init_sigma=3.0)):      # blur radius beyond the instantiated kernels
+        with pytest.raises(S.SiftError) as e:
+            ctx.detect(img, **bad)
+        assert e.value.code == 5, bad
     with pytest.raises(S.SiftError) as e:
         ctx.detect(np.zeros((64, 64, 2), np.uint8))
     assert e.value.code == 1
@@ -468,6 +470,31 @@ def test_non_default_arguments_vs_oracle(ctx, kw):
     rep = P.descriptor_report(got, want, gi, wi)
     REPORT["params_" + "_".join(f"{k}={v}" for k, v in sorted(kw.items()))[:60]] = dict(
         n_gpu=len(got), n_ref=len(want), recall=rec, precision=prec, desc=rep)
+    assert len(want) > 30
+    assert rec >= 0.99 and prec >= 0.99
+    assert rep["frac_le1"] >= 0.98
+
+
+@pytest.mark.parametrize("kw", [dict(intervals=2, contrast_threshold=0.05), dict(intervals=4, init_sigma=1.4, peak_ratio=0.75),
+                                dict(intervals=5), dict(intervals=2, double_image_size=False)])
+def test_other_interval_counts_vs_oracle(ctx, kw):
+    """intervals != 3: 5..8 Gaussian and 4..7 DoG layers per octave, the threshold
+    floor(0.5 ct / intervals * 255), the size formula and the next-octave base G[intervals] all follow."""
+    img = O.synth_image(300, 400, seed=33)
+    got = ctx.detect(img, **kw)
+    run = O.Run(O.best(), img, params=O.Params(**kw), keep_pyramid=True)
+    want = run.keypoints(2)
+    st = ctx.stats()
+    assert st["octaves"] == run.octaves
+    both, only_gpu, only_ref = P.set_diff_report(ctx.extrema(), run.extrema().astype(np.int64))
+    assert only_gpu + only_ref <= max(2, 0.005 * (both + only_ref))
+    L = kw["intervals"] + 3
+    worst = max(np.abs(ctx.dog(1, l) - run.dog(1, l)).max() for l in range(L - 1))
+    assert worst < 3e-4
+    rec, prec, gi, wi = P.recall_precision(got, want)
+    rep = P.descriptor_report(got, want, gi, wi)
+    REPORT["intervals_" + "_".join(f"{k}={v}" for k, v in sorted(kw.items()))[:50]] = dict(
+        n_gpu=len(got), n_ref=len(want), recall=rec, precision=prec, desc=rep, dog_err=worst)
     assert len(want) > 30
     assert rec >= 0.99 and prec >= 0.99
     assert rep["frac_le1"] >= 0.98
