@@ -110,3 +110,85 @@ def match_collection(local, n_images, ratio_threshold=0.75, ctx=None, matcher=No
             for p in parts:
                 result.update(p)
     return result
+
+
+# ------------------------------------------------------------------------------------------
+# Collection driver: the stitching datasets shipped with the reference
+# (stitching/collection/Dataset/*/) carry a "<name>-STITCH-GRAPH.txt" with lines such as
+#   {images_count | 21 | images count}
+#   {center_image_index | 4 | center image index}
+#   {matching_graph_image_edges-3 | 4,14 | matching graph image edge 3}
+# i.e. image 3 is to be matched against images 4 and 14.  The driver detects every image once and
+# matches exactly the listed edges (or all pairs when no graph is given).
+# ------------------------------------------------------------------------------------------
+def parse_stitch_graph(text):
+    """Returns (images_count, center_image_index, sorted list of (i, j) edges with i < j)."""
+    import re
+    count, center, edges = None, None, set()
+    for m in re.finditer(r"\{\s*([A-Za-z_]+)(?:-(\d+))?\s*\|\s*([^|]*?)\s*\|[^}]*\}", text):
+        key, idx, val = m.group(1), m.group(2), m.group(3)
+        if key == "images_count":
+            count = int(val)
+        elif key == "center_image_index":
+            center = int(val)
+        elif key == "matching_graph_image_edges" and idx is not None:
+            i = int(idx)
+            for tok in val.split(","):
+                tok = tok.strip()
+                if tok:
+                    j = int(tok)
+                    if i != j:
+                        edges.add((min(i, j), max(i, j)))
+    if count is None:
+        raise ValueError("no images_count entry in the stitch graph")
+    for i, j in edges:
+        if not (0 <= i < count and 0 <= j < count):
+            raise ValueError(f"edge ({i}, {j}) outside 0..{count - 1}")
+    return count, center, sorted(edges)
+
+
+def match_graph(ctx, keypoints, edges=None, ratio_threshold=0.75):
+    """keypoints: list of record arrays (one per image, from SiftContext.detect).  Returns
+    {(i, j): (idx_i, idx_j, dist)} for the listed edges (all pairs if edges is None)."""
+    n = len(keypoints)
+    if edges is None:
+        edges = pair_list(n)
+    descs = [np.ascontiguousarray(k["desc"]) for k in keypoints]
+    return {(i, j): ctx.match(descs[i], descs[j], ratio_threshold) for (i, j) in edges}
+
+
+def run_dataset(directory, device=0, ratio_threshold=0.75, all_pairs=False, **detect_params):
+    """Detect every image of a dataset directory and match its stitch graph.  Images are decoded
+    with PIL -- fine for a driver, but NOT pixel-identical to the reference's stb decoder on JPEGs;
+    parity runs feed stb-decoded pixels (tests/golden/make_golden.py)."""
+    import glob
+    import os
+    from PIL import Image
+    from .api import SiftContext
+
+    graphs = sorted(glob.glob(os.path.join(directory, "*STITCH-GRAPH.txt")))
+    files = sorted(f for f in glob.glob(os.path.join(directory, "*"))
+                   if f.lower().endswith((".jpg", ".jpeg", ".png", ".bmp")))
+    edges = None
+    if graphs and not all_pairs:
+        count, _, edges = parse_stitch_graph(open(graphs[0]).read())
+        if count != len(files):
+            raise ValueError(f"{graphs[0]} lists {count} images, the directory holds {len(files)}")
+    images = [np.asarray(Image.open(f).convert("RGB")) for f in files]
+    w = max(im.shape[1] for im in images)
+    h = max(im.shape[0] for im in images)
+    with SiftContext(w, h, device) as ctx:
+        kps = [ctx.detect(im, **detect_params) for im in images]
+        matches = match_graph(ctx, kps, edges, ratio_threshold)
+    return files, kps, matches
+
+
+if __name__ == "__main__":
+    import sys
+    if len(sys.argv) < 2:
+        sys.exit("usage: python -m sift_project_b200.collection <dataset directory> [--all-pairs]")
+    names, kps_, res = run_dataset(sys.argv[1], all_pairs="--all-pairs" in sys.argv[2:])
+    for f, k in zip(names, kps_):
+        print(f"{f}: {len(k)} keypoints")
+    for (i, j), (ia, ib, d) in sorted(res.items()):
+        print(f"edge {i}-{j}: {len(ia)} matches")

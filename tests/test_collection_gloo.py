@@ -81,3 +81,20 @@ def test_world2_collection_matches_single_process():
 def test_single_process_path_needs_a_context():
     with pytest.raises(ValueError):
         Cn.match_collection({0: torch.zeros((3, 128), dtype=torch.uint8)}, 1)
+
+
+def test_parse_stitch_graph():
+    text = """{center_image_index | 2 | center image index}
+{center_image_rotation_angle | 0 | center image rotation angle}
+{images_count | 5 | images count}
+{matching_graph_image_edges-0 | 1,4 | matching graph image edge 0}
+{matching_graph_image_edges-1 | 2 | matching graph image edge 1}
+{matching_graph_image_edges-3 | 4,2 | matching graph image edge 3}
+"""
+    count, center, edges = Cn.parse_stitch_graph(text)
+    assert (count, center) == (5, 2)
+    assert edges == [(0, 1), (0, 4), (1, 2), (2, 3), (3, 4)]
+    with pytest.raises(ValueError):
+        Cn.parse_stitch_graph("{matching_graph_image_edges-0 | 1 | x}")
+    with pytest.raises(ValueError):
+        Cn.parse_stitch_graph("{images_count | 2 | n}{matching_graph_image_edges-0 | 5 | x}")

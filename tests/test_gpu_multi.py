@@ -37,3 +37,32 @@ def test_drop_in_sift_binary(tmp_path):
     assert finals == [1286, 1430]          # SURVEY.md section 4 known answers
     assert (tmp_path / "matches.png").stat().st_size > 10000
     assert (tmp_path / "keypoints.png").stat().st_size > 10000
+
+
+def test_collection_driver_on_a_synthetic_dataset(tmp_path):
+    """overlapping crops of one scene + a STITCH-GRAPH file -> detect all, match
+    the listed edges; overlapping neighbours share many matches, and every edge equals the oracle."""
+    import numpy as np
+    from PIL import Image
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    from sift_project_b200 import collection as Cn
+    scene = O.synth_image(360, 900, seed=17)
+    offs = [0, 180, 360, 540]
+    for k, x in enumerate(offs):
+        Image.fromarray(scene[:, x:x + 360]).save(tmp_path / f"{k:02d}.png")
+    (tmp_path / "toy-STITCH-GRAPH.txt").write_text(
+        "{center_image_index | 1 | c}\n{images_count | 4 | n}\n"
+        "{matching_graph_image_edges-0 | 1 | e}\n{matching_graph_image_edges-1 | 2 | e}\n"
+        "{matching_graph_image_edges-2 | 3 | e}\n{matching_graph_image_edges-0 | 3 | e}\n")
+    files, kps, res = Cn.run_dataset(str(tmp_path))
+    assert len(files) == 4 and sorted(res) == [(0, 1), (0, 3), (1, 2), (2, 3)]
+    for (i, j), (ia, ib, d) in res.items():
+        wa, wb, wd = O.match(O.port(), kps[i]["desc"], kps[j]["desc"])
+        assert np.array_equal(ia, wa) and np.array_equal(ib, wb) and np.array_equal(d, wd)
+    assert min(len(res[e][0]) for e in ((0, 1), (1, 2), (2, 3))) > 100   # half-overlapping neighbours
+    assert len(res[(0, 3)][0]) < 20                                      # disjoint crops
+    # matched keypoints of overlapping crops sit 180 px apart in x
+    ia, ib, _ = res[(0, 1)]
+    dx = kps[0]["x"][ia] - kps[1]["x"][ib]
+    assert np.median(np.abs(dx - 180.0)) < 0.5
