@@ -498,3 +498,54 @@ def test_other_interval_counts_vs_oracle(ctx, kw):
     assert len(want) > 30
     assert rec >= 0.99 and prec >= 0.99
     assert rep["frac_le1"] >= 0.98
+
+
+def test_random_shapes_fused_equals_per_level(ctx):
+    """A sweep of awkward shapes (primes, thin strips, sizes around the 64 / 128 tile edges): the
+    fused input + cascade kernels and the per-level kernels must give identical bytes."""
+    rng = np.random.default_rng(2024)
+    shapes = [(67, 131), (64, 64), (65, 129), (127, 63), (129, 65), (40, 700), (500, 37), (193, 257), (255, 511)]
+    shapes += [(int(rng.integers(33, 400)), int(rng.integers(33, 640))) for _ in range(6)]
+    for h, w in shapes:
+        img = O.synth_image(h, w, seed=h * 1000 + w)
+        for doubled in (True, False):
+            ctx.debug_options(unfused_pyramid=True)
+            ref = ctx.detect(img, double_image_size=doubled)
+            ctx.debug_options(unfused_pyramid=False)
+            got = ctx.detect(img, double_image_size=doubled)
+            assert got.tobytes() == ref.tobytes(), (h, w, doubled)
+    ctx.debug_options()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_small_images_vs_oracle(ctx, seed):
+    rng = np.random.default_rng(seed)
+    h, w = int(rng.integers(90, 260)), int(rng.integers(90, 330))
+    img = O.synth_image(h, w, seed=seed + 500)
+    got = ctx.detect(img)
+    want = O.Run(O.best(), img, keep_pyramid=False).keypoints(2)
+    rec, prec, gi, wi = P.recall_precision(got, want)
+    rep = P.descriptor_report(got, want, gi, wi)
+    assert rec >= 0.99 and prec >= 0.99, (h, w, rec, prec)
+    assert rep["frac_le1"] >= 0.97
+
+
+def test_noise_and_dense_texture_images(ctx):
+    """iid noise (sparse: the DoG of white noise rarely clears the contrast threshold) and a fine
+    texture with ~4x the keypoint density of generator D (SURVEY.md 8d calibration)."""
+    from scipy.ndimage import gaussian_filter
+    rng = np.random.default_rng(9)
+    noise = rng.integers(0, 256, (384, 512), dtype=np.uint8)
+    acc = np.zeros((384, 512))
+    for s in (1, 2, 4, 8, 16):
+        n = gaussian_filter(rng.standard_normal((384, 512)), s, mode="wrap")
+        acc += n / n.std()
+    dense = np.rint((acc - acc.min()) / (acc.max() - acc.min()) * 255.0).astype(np.uint8)
+    for tag, img in (("iid_noise", noise), ("dense_texture", dense)):
+        got = ctx.detect(img)
+        st = ctx.stats()
+        want = O.Run(O.best(), img, keep_pyramid=False).keypoints(2)
+        rec, prec, gi, wi = P.recall_precision(got, want)
+        REPORT[tag] = dict(stats=st, n_ref=len(want), recall=rec, precision=prec)
+        assert rec >= 0.99 and prec >= 0.99, tag
+    assert st["final_keypoints"] > 2000
