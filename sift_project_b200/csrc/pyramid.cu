@@ -85,10 +85,8 @@ k_blur(const float* __restrict__ in, float* __restrict__ out, float* __restrict_
         for (int k = 0; k < 4; ++k) {
             float acc = 0.f;
 #pragma unroll
-#ifndef SB_EXP_SKIP_H   // (scratch experiments only)
             for (int u = R; u >= 1; --u)  // outermost (smallest) taps first
                 acc = fmaf(taps.w[u], v[G::HX + k - u] + v[G::HX + k + u], acc);
-#endif
             o[k] = fmaf(taps.w[0], v[G::HX + k], acc);
         }
         *reinterpret_cast<float4*>(s_tmp + r * TW + 4 * lane) = make_float4(o[0], o[1], o[2], o[3]);
@@ -106,11 +104,7 @@ k_blur(const float* __restrict__ in, float* __restrict__ out, float* __restrict_
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int d = (r - k - R) < 0 ? (k + R - r) : (r - k - R);
-#ifdef SB_EXP_SKIP_V
-                if (d == 0) {
-#else
                 if (d <= R) {
-#endif
                     const float wt = taps.w[d];
                     acc[k].x = fmaf(wt, t.x, acc[k].x);
                     acc[k].y = fmaf(wt, t.y, acc[k].y);
@@ -211,10 +205,8 @@ __device__ __forceinline__ void cascade_hpass(const float* __restrict__ in, floa
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             float acc = 0.f;
-#ifndef SB_EXP_SKIP_H   // (scratch experiments only)
 #pragma unroll
             for (int u = R; u >= 1; --u) acc = fmaf(taps.w[u], v[HXR + k - u] + v[HXR + k + u], acc);
-#endif
             o[k] = fmaf(taps.w[0], v[HXR + k], acc);
         }
         *reinterpret_cast<float4*>(out + r * OUT_W + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
@@ -242,11 +234,7 @@ __device__ __forceinline__ void cascade_vpass(const float* __restrict__ tmp, int
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int d = (r - k - R) < 0 ? (k + R - r) : (r - k - R);
-#ifdef SB_EXP_SKIP_V
-                if (d == 0) {
-#else
                 if (d <= R) {
-#endif
                     lo[k] = __ffma2_rn(w2[d], tl, lo[k]);
                     hi[k] = __ffma2_rn(w2[d], th, hi[k]);
                 }
