@@ -44,10 +44,10 @@ typedef struct sift_b200_keypoint {
 } sift_b200_keypoint;
 
 /* The arguments of detect_keypoints_and_descriptors (sift.hh:65-71), same meaning and defaults.
- * This build implements intervals in 2..5, window_size == 3, num_bins == 36 (window and bins are
- * the reference's defaults; get_pixel_cube is hard-wired to 3x3x3 there too, sift.cpp:35-37); other
- * values, and init_sigma / intervals combinations whose blur radius exceeds 16, return
- * SIFT_B200_E_UNSUPPORTED.  The fused per-octave kernels serve the default sigmas; other settings
+ * This build implements intervals in 2..5, odd window_size in 3..7 (as long as a DoG layer is left
+ * to test; the fit itself stays 3x3x3 like the reference's get_pixel_cube, sift.cpp:35-37) and
+ * num_bins in 4..128; other values, and init_sigma / intervals combinations whose blur radius
+ * exceeds 16, return SIFT_B200_E_UNSUPPORTED.  The fused per-octave kernels serve the default sigmas; other settings
  * run one blur kernel per level (same arithmetic).  max_octaves is an extension: 0 = derive as the reference does
  * (sift.cpp:132-137), n > 0 = stop after n octaves. */
 typedef struct sift_b200_params {

@@ -51,12 +51,14 @@ class Params(C.Structure):
     """OracleParams / RefParams: the tunable arguments of sift.hh:65-71."""
     _fields_ = [("double_image_size", C.c_int32), ("init_sigma", C.c_double), ("intervals", C.c_int32),
                 ("contrast_threshold", C.c_double), ("eigen_ratio", C.c_double), ("peak_ratio", C.c_double),
-                ("ori_sigma_factor", C.c_double), ("desc_scale_factor", C.c_double)]
+                ("ori_sigma_factor", C.c_double), ("desc_scale_factor", C.c_double),
+                ("window_size", C.c_int32), ("num_bins", C.c_double)]
 
     def __init__(self, double_image_size=True, init_sigma=1.6, intervals=3, contrast_threshold=0.04,
-                 eigen_ratio=10.0, peak_ratio=0.8, ori_sigma_factor=1.5, desc_scale_factor=3.0):
+                 eigen_ratio=10.0, peak_ratio=0.8, ori_sigma_factor=1.5, desc_scale_factor=3.0, window_size=3,
+                 num_bins=36):
         super().__init__(int(bool(double_image_size)), init_sigma, intervals, contrast_threshold, eigen_ratio,
-                         peak_ratio, ori_sigma_factor, desc_scale_factor)
+                         peak_ratio, ori_sigma_factor, desc_scale_factor, window_size, num_bins)
 
 
 class _Lib:

@@ -19,7 +19,6 @@ namespace {
 constexpr double kPi = 3.14159265358979323846;  // M_PI
 constexpr double kTwoPi = 6.283185307179586;    // M_PI2, sift.hh:5
 constexpr int kMaxSteps = 5;                    // sift.hh:7
-constexpr int kBins = 36;                       // sift.hh:69
 
 struct Plane {
     int w = 0, h = 0;
@@ -114,13 +113,14 @@ struct Cand { double x, y; int z, o; };  // sift.cpp:14
 
 using Octave = std::vector<Plane>;
 
-// sift.cpp:227-256 -- tie-tolerant 26-neighbour test (only strict orderings disqualify).
-bool extremum26(const Octave& D, int x, int y, int z) {
+// sift.cpp:227-256 -- tie-tolerant test over the (2 border + 1)^3 cube (only strict orderings
+// disqualify); border = window_size / 2.
+bool extremum_cube(const Octave& D, int x, int y, int z, int border) {
     bool mx = true, mn = true;
     double c = D[z].at(x, y);
-    for (int dz = -1; dz <= 1; ++dz)
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx) {
+    for (int dz = -border; dz <= border; ++dz)
+        for (int dy = -border; dy <= border; ++dy)
+            for (int dx = -border; dx <= border; ++dx) {
                 if (!dx && !dy && !dz) continue;
                 double n = D[z + dz].at(x + dx, y + dy);
                 if (c < n) mx = false;
@@ -234,13 +234,14 @@ void build_pyramid(OracleRun& r, const double* px, int w, int h, int c, bool dou
 void scan_extrema(OracleRun& r) {
     const int kIntervals = r.p.intervals, kDogs = r.dogs();
     const int thr = (int)std::floor(0.5 * r.p.contrast_threshold / (double)kIntervals * 255.0);
+    const int border = r.p.window_size / 2;  // sift.cpp:272
     for (int o = 0; o < (int)r.D.size(); ++o) {
         const Octave& D = r.D[o];
-        for (int x = 1; x < D[0].w - 1; ++x)
-            for (int y = 1; y < D[0].h - 1; ++y)
-                for (int z = 1; z < kDogs - 1; ++z) {
+        for (int x = border; x < D[0].w - border; ++x)
+            for (int y = border; y < D[0].h - border; ++y)
+                for (int z = border; z < kDogs - border; ++z) {
                     if (std::abs(D[z].at(x, y)) <= thr) continue;
-                    if (extremum26(D, x, y, z)) r.extrema.push_back({(double)x, (double)y, z, o});
+                    if (extremum_cube(D, x, y, z, border)) r.extrema.push_back({(double)x, (double)y, z, o});
                 }
     }
 }
@@ -249,6 +250,7 @@ void scan_extrema(OracleRun& r) {
 void refine(OracleRun& r) {
     const double contrast = r.p.contrast_threshold, ratio = r.p.eigen_ratio, sigma0 = r.p.init_sigma;
     const int kIntervals = r.p.intervals, kDogs = r.dogs();
+    const int border = r.p.window_size / 2;  // sift.cpp:336
     for (const Cand& e : r.extrema) {
         const Octave& D = r.D[e.o];
         const int W = D[0].w, H = D[0].h;
@@ -277,7 +279,8 @@ void refine(OracleRun& r) {
             layer = (int)(layer + std::round(f.off[0]));
             x += std::round(f.off[1]);
             y += std::round(f.off[2]);
-            if (x < 1 || x >= W - 1 || y < 1 || y >= H - 1 || layer < 1 || layer >= kDogs - 1) break;
+            if (x < border || x >= W - border || y < border || y >= H - border || layer < border ||
+                layer >= kDogs - border) break;  // sift.cpp:405-410
         }
         if (!keep) continue;
         double s = std::pow(2, e.o);
@@ -296,6 +299,7 @@ void refine(OracleRun& r) {
 // sift.cpp:447-533
 void orient(OracleRun& r, bool doubled) {
     const double peak_ratio = r.p.peak_ratio, factor = r.p.ori_sigma_factor;
+    const int kBins = (int)r.p.num_bins;  // declared double, used as int (sift.cpp:450)
     for (const OracleKeypoint& kp : r.raw) {
         double inv = 1.0 / std::pow(2, kp.octave);
         int x = (int)std::round(kp.x * inv), y = (int)std::round(kp.y * inv);
@@ -303,7 +307,8 @@ void orient(OracleRun& r, bool doubled) {
         int radius = (int)std::round(3.0 * scale);
         double denom = 2.0 * scale * scale;
         const Plane& I = r.G[kp.octave][kp.layer];
-        double hist[kBins] = {0};
+        std::vector<double> hist_v(kBins, 0.0);
+        double* hist = hist_v.data();
         for (int i = -radius; i <= radius; ++i) {
             if (x + i - 1 < 0 || x + i + 1 >= I.w) continue;
             for (int j = -radius; j <= radius; ++j) {
@@ -413,6 +418,7 @@ extern "C" {
 void oracle_default_params(OracleParams* p) {
     p->double_image_size = 1; p->init_sigma = 1.6; p->intervals = 3; p->contrast_threshold = 0.04;
     p->eigen_ratio = 10.0; p->peak_ratio = 0.8; p->ori_sigma_factor = 1.5; p->desc_scale_factor = 3.0;
+    p->window_size = 3; p->num_bins = 36;
 }
 
 OracleRun* oracle_run_create(const double* pixels, int w, int h, int c, int double_image_size,

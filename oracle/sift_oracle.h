@@ -26,13 +26,14 @@ typedef struct OracleKeypoint {
     uint8_t desc[128];
 } OracleKeypoint;
 
-/* The tunable arguments of detect_keypoints_and_descriptors (sift.hh:65-71); window_size and
- * num_bins stay at the reference defaults (3, 36). */
+/* The arguments of detect_keypoints_and_descriptors (sift.hh:65-71). */
 typedef struct OracleParams {
     int32_t double_image_size;
     double init_sigma;
     int32_t intervals;
     double contrast_threshold, eigen_ratio, peak_ratio, ori_sigma_factor, desc_scale_factor;
+    int32_t window_size;
+    double num_bins;
 } OracleParams;
 void oracle_default_params(OracleParams* p);
 

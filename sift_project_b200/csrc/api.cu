@@ -157,9 +157,12 @@ size_t arena_need(int bw, int bh, int planes = kLayers + kDogs) {
 }
 
 int check_params(sift_b200_ctx* c, const sift_b200_params& p) {
-    if (p.intervals < 2 || p.intervals > kMaxIntervals || p.window_size != 3 || p.num_bins != 36.0)
+    const int bins = (int)p.num_bins;  // declared double, used as int (sift.cpp:450)
+    if (p.intervals < 2 || p.intervals > kMaxIntervals || p.window_size < 3 || p.window_size > 7 ||
+        !(p.window_size & 1) || 2 * (p.window_size / 2) >= p.intervals + 2 || bins < 4 || bins > 128)
         return fail(c, SIFT_B200_E_UNSUPPORTED,
-                    "this build implements intervals in 2..%d, window_size=3, num_bins=36 (got %d, %d, %g)",
+                    "this build implements intervals in 2..%d, odd window_size in 3..7 that leaves a layer to "
+                    "test, num_bins in 4..128 (got %d, %d, %g)",
                     kMaxIntervals, p.intervals, p.window_size, p.num_bins);
     if (!(p.init_sigma > 1.0) || p.init_sigma > 3.0)
         return fail(c, SIFT_B200_E_UNSUPPORTED, "init_sigma must be in (1, 3] (got %g)", p.init_sigma);
@@ -253,6 +256,8 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     sp.doubled = doubled;
     sp.intervals = p.intervals;
     sp.dogs = dogs;
+    sp.num_bins = (int)p.num_bins;
+    sp.border = p.window_size / 2;
     sp.dog_threshold = (int)floor(0.5 * p.contrast_threshold / p.intervals * 255.0);  // sift.cpp:305-307
     sp.init_sigma = p.init_sigma;
     sp.contrast_threshold = p.contrast_threshold;
@@ -333,8 +338,8 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
         }
         prof_mark(c, SIFT_B200_STAGE_PYRAMID, layers - 1);
         }
-        if (od.w >= 3 && od.h >= 3) {
-            CU(c, launch_extrema(od, o, dogs, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, s));
+        if (od.w >= 2 * sp.border + 1 && od.h >= 2 * sp.border + 1) {
+            CU(c, launch_extrema(od, o, dogs, sp.border, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, s));
             prof_mark(c, SIFT_B200_STAGE_EXTREMA, 1);
         }
     }

@@ -66,6 +66,8 @@ struct StageParams {
     int doubled;
     int intervals;
     int dogs;                 // intervals + 2
+    int num_bins;             // orientation histogram bins (declared double, used as int, sift.cpp:450)
+    int border;               // window_size / 2 (sift.cpp:272, :336)
     int dog_threshold;        // floor(0.5*ct/intervals*255) squeezed into an int (sift.cpp:266,305)
     double init_sigma;
     double contrast_threshold;

@@ -132,6 +132,35 @@ k_extrema(const OctaveDesc oct, int octave, float thr, Cand* __restrict__ cands,
     }
 }
 
+// Generic window (window_size = 5, 7: border = 2, 3): the same tie-tolerant test over the
+// (2 border + 1)^3 cube, thread per pixel, neighbours straight from L1/L2.  Rarely used knob; the
+// 3x3x3 default takes the register-window kernel above.
+__global__ void __launch_bounds__(256)
+k_extrema_window(const OctaveDesc oct, int octave, int dogs, int border, float thr, Cand* __restrict__ cands,
+                 int cap, Counters* __restrict__ counters) {
+    const int x = border + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = border + blockIdx.y;
+    if (x >= oct.w - border || y >= oct.h - border) return;
+    for (int z = border; z < dogs - border; ++z) {
+        const float c = ldg(oct.D[z] + (size_t)y * oct.pitch + x);
+        if (!(fabsf(c) > thr)) continue;
+        bool mx = true, mn = true;
+        for (int dz = -border; dz <= border && (mx || mn); ++dz)
+            for (int dy = -border; dy <= border; ++dy) {
+                const float* row = oct.D[z + dz] + (size_t)(y + dy) * oct.pitch + x;
+                for (int dx = -border; dx <= border; ++dx) {
+                    const float v = ldg(row + dx);
+                    mx = mx && !(c < v);
+                    mn = mn && !(c > v);
+                }
+            }
+        if (mx || mn) {
+            const int slot = atomicAdd(&counters->n_extrema, 1);
+            if (slot < cap) cands[slot] = Cand{x, y, z, octave};
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Refinement -- sift.cpp:330-436 (compute_keypoints) with get_pixel_cube :32-44,
 // compute_gradient :49-55, compute_hessian :60-80, fit_quadratic :86-106.  FP64, one thread per
@@ -206,7 +235,8 @@ k_refine(const PyramidDesc* __restrict__ pyr, const Cand* __restrict__ cands, Kp
             layer += (int)round(f.off[0]);
             x += (int)round(f.off[1]);
             y += (int)round(f.off[2]);
-            if (x < 1 || x >= oc.w - 1 || y < 1 || y >= oc.h - 1 || layer < 1 || layer >= sp.dogs - 1) break;
+            if (x < sp.border || x >= oc.w - sp.border || y < sp.border || y >= oc.h - sp.border ||
+                layer < sp.border || layer >= sp.dogs - sp.border) break;  // sift.cpp:405-410
         }
         if (!keep) continue;
         const double s = (double)(1 << e.o);  // pow(2, octave)
@@ -231,17 +261,24 @@ k_refine(const PyramidDesc* __restrict__ pyr, const Cand* __restrict__ cands, Kp
 // for pixel values in [0, 255], which is mapped to 2^32.
 // ------------------------------------------------------------------------------------------
 constexpr int ORI_COPIES = 8;
+constexpr int kMaxOriBins = 128;   // largest num_bins of the generic instantiation
 
+// NB > 0: compile-time bin count (36, the reference default: smoothing stays in registers);
+// NB == 0: sp.num_bins at run time (<= kMaxOriBins), smoothing through shared memory.
+template <int NB>
 __global__ void __launch_bounds__(256, 2)
 k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, KpCore* __restrict__ oriented,
          Counters* __restrict__ counters, const StageParams sp) {
-    __shared__ unsigned s_hist[8][ORI_COPIES][kOriBins];
-    __shared__ double s_smooth[8][kOriBins];
+    constexpr int CAPB = NB > 0 ? NB : kMaxOriBins;
+    constexpr int COPIES = NB > 0 ? ORI_COPIES : 2;
+    __shared__ unsigned s_hist[8][COPIES][CAPB];
+    __shared__ double s_smooth[8][CAPB];
+    const int nb = NB > 0 ? NB : sp.num_bins;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* smooth = s_smooth[warp];
     const int n = min(counters->n_raw, sp.cap_raw);
     unsigned* hist = &s_hist[warp][0][0];
-    unsigned* my_hist = s_hist[warp][lane & (ORI_COPIES - 1)];
+    unsigned* my_hist = s_hist[warp][lane & (COPIES - 1)];
     // keypoints cost 4x more or less than one another: warps pull the next one from a shared cursor
     for (;;) {
         int i = 0;
@@ -261,7 +298,8 @@ k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, Kp
         const double bound = g1 * g1 * 361.0;
         const float fix = (float)(4294967296.0 / bound);
         const double unfix = bound / 4294967296.0;
-        for (int b = lane; b < ORI_COPIES * kOriBins; b += 32) hist[b] = 0u;
+        const float bins_per_rad = (float)nb * (1.0f / 6.283185307179586f);
+        for (int b = lane; b < COPIES * CAPB; b += 32) hist[b] = 0u;
         __syncwarp();
         // window clipped to the pixels whose 4-neighbourhood is inside the image (sift.cpp:473,478)
         const int i_lo = max(-radius, 1 - x), i_hi = min(radius, W - 2 - x);
@@ -279,50 +317,62 @@ k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, Kp
             const float mag = g2 > 0.f ? g2 * rsqrtf(g2) : 0.f;
             const float ang = fast_atan2(dy, dx);
             const float wgt = __expf((float)(i_off * i_off + j_off * j_off) * neg_inv_denom);
-            int b = (int)roundf((float)kOriBins * (ang + 3.14159265358979323846f) * (1.0f / 6.283185307179586f));
-            b = (b < kOriBins) ? b : 0;  // sift.cpp:489-490: bin 0 <-> angle -pi
+            int b = (int)roundf((ang + 3.14159265358979323846f) * bins_per_rad);
+            b = (b < nb) ? b : 0;  // sift.cpp:489-490: bin 0 <-> angle -pi
             b = max(b, 0);
             atomicAdd(&my_hist[b], __float2uint_rn(wgt * mag * fix));
         }
         __syncwarp();
         // lane 0 smooths (the reference's in-place, sequential 1/4-1/2-1/4 filter, sift.cpp:496-504:
-        // bin i sees the already-updated bin i-1, and bin 35 the already-updated bin 0), fully
-        // unrolled so the 36 values stay in registers; all lanes then test their bins for peaks.
+        // bin i sees the already-updated bin i-1, and the last bin the already-updated bin 0); with
+        // a compile-time bin count the loop is fully unrolled and the values stay in registers.
+        // All lanes then test their bins for peaks.
         if (lane == 0) {
-            double hd[kOriBins];
+            if (NB > 0) {
+                double hd[CAPB];
 #pragma unroll
-            for (int b = 0; b < kOriBins; ++b) {
-                unsigned long long t = 0;
+                for (int b = 0; b < CAPB; ++b) {
+                    unsigned long long t = 0;
 #pragma unroll
-                for (int cpy = 0; cpy < ORI_COPIES; ++cpy) t += hist[cpy * kOriBins + b];
-                hd[b] = (double)t * unfix;
+                    for (int cpy = 0; cpy < COPIES; ++cpy) t += hist[cpy * CAPB + b];
+                    hd[b] = (double)t * unfix;
+                }
+#pragma unroll
+                for (int it = 0; it < 2; ++it)  // ORI_SMOOTH_ITERATIONS
+#pragma unroll
+                    for (int b = 0; b < CAPB; ++b)
+                        hd[b] = 0.25 * hd[(b + CAPB - 1) % CAPB] + 0.5 * hd[b] + 0.25 * hd[(b + 1) % CAPB];
+#pragma unroll
+                for (int b = 0; b < CAPB; ++b) smooth[b] = hd[b];
+            } else {
+                for (int b = 0; b < nb; ++b) {
+                    unsigned long long t = 0;
+                    for (int cpy = 0; cpy < COPIES; ++cpy) t += hist[cpy * CAPB + b];
+                    smooth[b] = (double)t * unfix;
+                }
+                for (int it = 0; it < 2; ++it)
+                    for (int b = 0; b < nb; ++b)
+                        smooth[b] = 0.25 * smooth[(b + nb - 1) % nb] + 0.5 * smooth[b] + 0.25 * smooth[(b + 1) % nb];
             }
-#pragma unroll
-            for (int it = 0; it < 2; ++it)  // ORI_SMOOTH_ITERATIONS
-#pragma unroll
-                for (int b = 0; b < kOriBins; ++b)
-                    hd[b] = 0.25 * hd[(b + kOriBins - 1) % kOriBins] + 0.5 * hd[b] + 0.25 * hd[(b + 1) % kOriBins];
-#pragma unroll
-            for (int b = 0; b < kOriBins; ++b) smooth[b] = hd[b];
         }
         __syncwarp();
-        double top = fmax(smooth[lane], (lane + 32 < kOriBins) ? smooth[lane + 32] : 0.0);
+        double top = 0.0;
+        for (int b = lane; b < nb; b += 32) top = fmax(top, smooth[b]);
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) top = fmax(top, __shfl_xor_sync(0xffffffffu, top, d));
-#pragma unroll
-        for (int rep = 0; rep < 2; ++rep) {
-            const int b = lane + 32 * rep;
+        for (int b0 = 0; b0 < nb; b0 += 32) {
+            const int b = b0 + lane;
             bool peak = false;
             double ori = 0.0;
-            if (b < kOriBins) {
-                const double h0 = smooth[(b + kOriBins - 1) % kOriBins], h1 = smooth[b], h2 = smooth[(b + 1) % kOriBins];
+            if (b < nb) {
+                const double h0 = smooth[(b + nb - 1) % nb], h1 = smooth[b], h2 = smooth[(b + 1) % nb];
                 if (h1 > h0 && h1 > h2 && h1 > (sp.peak_ratio * top)) {
                     peak = true;
                     // fmod(t, m) for t in [0, 2m) is t or t - m, both exact
                     double pos = (double)b + 0.5 * (h0 - h2) / (h0 - 2 * h1 + h2);
-                    pos = pos + (double)kOriBins;
-                    if (pos >= (double)kOriBins) pos -= (double)kOriBins;
-                    ori = kTwoPi * pos / kOriBins;
+                    pos = pos + (double)nb;
+                    if (pos >= (double)nb) pos -= (double)nb;
+                    ori = kTwoPi * pos / nb;
                     ori = ori + kTwoPi;
                     if (ori >= kTwoPi) ori -= kTwoPi;
                 }
@@ -664,9 +714,14 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
 
 }  // namespace
 
-cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int threshold, Cand* cands, int cap,
-                           Counters* counters, cudaStream_t s) {
-    if (oct.w < 3 || oct.h < 3) return cudaSuccess;
+cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int border, int threshold, Cand* cands,
+                           int cap, Counters* counters, cudaStream_t s) {
+    if (oct.w < 2 * border + 1 || oct.h < 2 * border + 1) return cudaSuccess;
+    if (border != 1) {
+        dim3 grid((oct.w - 2 * border + 255) / 256, oct.h - 2 * border);
+        k_extrema_window<<<grid, 256, 0, s>>>(oct, octave, dogs, border, (float)threshold, cands, cap, counters);
+        return cudaGetLastError();
+    }
     const bool big = (long long)oct.w * oct.h >= (16ll << 20);
     dim3 grid((oct.w - 2 + 29) / 30, (oct.h - 2 + 8 * (big ? 32 : 8) - 1) / (8 * (big ? 32 : 8)));
 #define SB_EX(ND)                                                                                            \
@@ -690,7 +745,10 @@ cudaError_t launch_refine(const PyramidDesc* d_pyr, const Cand* cands, KpCore* r
 
 cudaError_t launch_orient(const PyramidDesc* d_pyr, const KpCore* raw, KpCore* oriented, Counters* counters,
                           const StageParams& sp, cudaStream_t s) {
-    k_orient<<<148 * 4, 256, 0, s>>>(d_pyr, raw, oriented, counters, sp);
+    if (sp.num_bins == kOriBins)
+        k_orient<kOriBins><<<148 * 4, 256, 0, s>>>(d_pyr, raw, oriented, counters, sp);
+    else
+        k_orient<0><<<148 * 4, 256, 0, s>>>(d_pyr, raw, oriented, counters, sp);
     return cudaGetLastError();
 }
 

@@ -33,8 +33,8 @@ struct SortScratch {
     int* sorted;        // [cap_oriented]
     int* final_order;   // [cap_oriented]
 };
-cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int threshold, Cand* cands, int cap,
-                           Counters* counters, cudaStream_t s);
+cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int border, int threshold, Cand* cands,
+                           int cap, Counters* counters, cudaStream_t s);
 cudaError_t launch_refine(const PyramidDesc* d_pyr, const Cand* cands, KpCore* raw,
                           Counters* counters, const StageParams& sp, cudaStream_t s);
 cudaError_t launch_orient(const PyramidDesc* d_pyr, const KpCore* raw, KpCore* oriented,

@@ -237,7 +237,8 @@ def test_flat_image_has_no_keypoints(ctx):
 
 def test_error_behaviour(ctx):
     img = O.synth_image(64, 64, seed=1)
-    for bad in (dict(intervals=1), dict(intervals=6), dict(window_size=5), dict(num_bins=18),
+    for bad in (dict(intervals=1), dict(intervals=6), dict(window_size=4), dict(window_size=9), dict(num_bins=2),
+                dict(window_size=5, intervals=2),        # no DoG layer left between the borders
                 dict(intervals=2, init_sigma=3.0)):      # blur radius beyond the instantiated kernels
         with pytest.raises(S.SiftError) as e:
             ctx.detect(img, **bad)
@@ -549,3 +550,23 @@ def test_noise_and_dense_texture_images(ctx):
         REPORT[tag] = dict(stats=st, n_ref=len(want), recall=rec, precision=prec)
         assert rec >= 0.99 and prec >= 0.99, tag
     assert st["final_keypoints"] > 2000
+
+
+@pytest.mark.parametrize("kw", [dict(num_bins=18), dict(num_bins=72, peak_ratio=0.7), dict(window_size=5, intervals=4),
+                                dict(window_size=5, contrast_threshold=0.02)])
+def test_window_and_bin_counts_vs_oracle(ctx, kw):
+    """window_size and num_bins: (2b+1)^3 tie-tolerant extrema with border b in the
+    scan and in the refinement bounds; orientation histograms with other bin counts."""
+    img = O.synth_image(300, 400, seed=35)
+    got = ctx.detect(img, **kw)
+    run = O.Run(O.best(), img, params=O.Params(**kw), keep_pyramid=False)
+    want = run.keypoints(2)
+    both, only_gpu, only_ref = P.set_diff_report(ctx.extrema(), run.extrema().astype(np.int64))
+    assert only_gpu + only_ref <= max(2, 0.005 * (both + only_ref))
+    rec, prec, gi, wi = P.recall_precision(got, want)
+    rep = P.descriptor_report(got, want, gi, wi)
+    REPORT["knobs_" + "_".join(f"{k}={v}" for k, v in sorted(kw.items()))[:50]] = dict(
+        n_gpu=len(got), n_ref=len(want), recall=rec, precision=prec, desc=rep)
+    assert len(want) > 30
+    assert rec >= 0.99 and prec >= 0.99
+    assert rep["frac_le1"] >= 0.98

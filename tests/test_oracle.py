@@ -149,6 +149,8 @@ PARAM_SETS = [
          ori_sigma_factor=1.8, desc_scale_factor=3.5),
     dict(intervals=2, contrast_threshold=0.05),
     dict(intervals=4, init_sigma=1.4, peak_ratio=0.75),
+    dict(num_bins=18), dict(num_bins=72, peak_ratio=0.7), dict(window_size=5, intervals=4),
+    dict(window_size=5, contrast_threshold=0.02),
 ]
 
 
