@@ -6,22 +6,27 @@
 // top-2 reduction over j runs straight out of tensor memory -- the N1 x N2 distance matrix is
 // never materialised.
 //
-// One persistent CTA per SM, 10 warps:
-//   warp 0      TMA producer: A tile (128 descriptors, resident per work item) and a 4-stage ring of
-//               B tiles (256 descriptors = 32 KB each); 128-byte rows land 128B-swizzled, which is
-//               exactly the K-major SWIZZLE_128B operand layout of tcgen05.mma.
-//   warp 1      MMA issuer: per B tile four tcgen05.mma.kind::i8 (M128 x N256 x K32) into one of two
-//               256-column TMEM accumulators; tcgen05.commit releases the smem stage and publishes
-//               the accumulator.
-//   warps 2..9  epilogue: each warp owns 32 TMEM lanes (rows) x 128 columns; tcgen05.ld 32 columns
-//               at a time, key = ((||b_j||^2 - 2 a.b_j) << 8) | (j & 255) with ONE integer
-//               multiply-add per element against a precomputed per-column constant, then ONE
-//               compare against the row's running second-best; only elements that beat it (a few
-//               per thousand after warm-up) take the branch that updates (best, second).  Keys order
-//               by (distance, column) so the reference's "lowest j wins ties" falls out of min().
-// Work items are (128-row block of A) x (split of the B tiles); partial (best, second) per split are
-// merged in ascending-j order by k_match_merge (match_simt.cu), then the shared emit kernel applies
-// Lowe's ratio test.
+// One persistent CTA per SM, 18 warps:
+//   warp 0       TMA producer: A tile (128 descriptors, resident per segment) and a 4-stage ring of
+//                B tiles (256 descriptors = 32 KB each); 128-byte rows land 128B-swizzled, which is
+//                exactly the K-major SWIZZLE_128B operand layout of tcgen05.mma.
+//   warp 1       MMA issuer: per B tile four tcgen05.mma.kind::i8 (M128 x N256 x K32) into one of two
+//                256-column TMEM accumulators; tcgen05.commit releases the smem stage and publishes
+//                the accumulator.
+//   warps 2..17  epilogue: each warp owns 32 TMEM lanes (rows) x 64 columns, tcgen05.ld 16 columns at a
+//                time (double-buffered).  K is only 128, so the kernel is epilogue-paced and every
+//                accumulator must cost as few issue slots as possible:
+//                  * pre-filter on the raw dot product: key_j < bound  =>  dot_j > theta (a 3-input
+//                    max tree over 16 values and one compare, no shared-memory traffic);
+//                  * only groups that pass form exact keys ((||b_j||^2 - 2 a.b_j) << 8) | (j & 255)
+//                    (one IMAD each) and merge their two smallest into the row's running
+//                    (best, second) with a short tournament.  Keys order by (distance, column), so
+//                    the reference's "lowest j wins ties" falls out of integer min();
+//                  * the four column slices of a row exchange (best, second) once per tile so that
+//                    each filters against the row's second best over ALL columns seen so far.
+// The flattened (row block x B tile) grid is cut into one contiguous range per CTA; a range is
+// walked as segments (runs inside one row block) whose partial (index, d1, d2) are merged in column
+// order by k_match_tc_merge, then the shared emit kernel applies Lowe's ratio test.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <limits.h>
