@@ -57,7 +57,12 @@ def all_gather_descriptors(local, n_images, group=None, device=None):
     mine = sorted(local)
     assert all(owner_of(i, world) == rank for i in mine), "a rank may only hold the images it owns"
     if device is None:
-        device = next(iter(local.values())).device if local else torch.device("cpu")
+        if local:
+            device = next(iter(local.values())).device
+        elif dist.is_initialized() and dist.get_backend(group) == "nccl":
+            device = torch.device("cuda", torch.cuda.current_device())   # a rank may own no image
+        else:
+            device = torch.device("cpu")
     counts = torch.zeros(n_images, dtype=torch.int64, device=device)
     for i in mine:
         counts[i] = local[i].shape[0]
@@ -86,7 +91,7 @@ def all_gather_descriptors(local, n_images, group=None, device=None):
 
 
 def match_collection(local, n_images, ratio_threshold=0.75, ctx=None, matcher=None, group=None,
-                     both_directions=False, gather_to_rank0=True):
+                     both_directions=False, gather_to_rank0=True, device=None):
     """All-pairs Lowe-ratio matching of a collection.  Returns {(i, j): (idx_i, idx_j, dist)};
     complete on rank 0 (when gather_to_rank0), this rank's share elsewhere."""
     import torch.distributed as dist
@@ -97,7 +102,7 @@ def match_collection(local, n_images, ratio_threshold=0.75, ctx=None, matcher=No
         if ctx is None:
             raise ValueError("match_collection needs a SiftContext (there is no CPU matcher in the product)")
         matcher = lambda a, b: ctx.match(a, b, ratio_threshold)  # noqa: E731
-    descs, counts = all_gather_descriptors(local, n_images, group=group)
+    descs, counts = all_gather_descriptors(local, n_images, group=group, device=device)
     mine = partition_pairs(counts, world, both_directions)[rank]
     result = {}
     for (i, j) in mine:

@@ -37,7 +37,7 @@ def _free_port():
 
 def _sets(n_images):
     rng = np.random.default_rng(0)
-    return [O.synth_descriptors(int(rng.integers(0, 90)) if i != 2 else 0, seed=100 + i) for i in range(n_images)]
+    return [O.synth_descriptors(int(rng.integers(1, 90)) if i != 2 else 0, seed=100 + i) for i in range(n_images)]
 
 
 def _worker(rank, world, port, n_images, q):
@@ -59,8 +59,9 @@ def _worker(rank, world, port, n_images, q):
         dist.destroy_process_group()
 
 
-def test_world2_collection_matches_single_process():
-    n_images, world = 7, 2
+@pytest.mark.parametrize("n_images", [7, 1])   # 1 image: rank 1 owns nothing
+def test_world2_collection_matches_single_process(n_images):
+    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
