@@ -88,7 +88,8 @@ const char* sift_b200_last_error(const sift_b200_ctx* ctx); /* ctx may be NULL: 
 /* detect_keypoints_and_descriptors (sift.cpp:712-776).
  * pixels: row-major, interleaved, channels = 1 (gray) or 3 (RGB), values 0..255; HOST or DEVICE
  * memory (detected).  The u8 entry point is exact for file-loaded images (image_io.cpp:27-33);
- * the f32 one accepts arbitrary values.  out: HOST array of `capacity` records, filled in the
+ * the f32 one accepts arbitrary finite values of any range (its min / max are reduced on the GPU to
+ * scale the fixed-point histograms; note that contrast_threshold assumes a 0..255 scale, sift.cpp:305).  out: HOST array of `capacity` records, filled in the
  * reference's order (sorted by Keypoint::operator<, sift.hh:31-41, duplicates removed).
  * *count receives the number found even when it exceeds capacity (status E_CAPACITY then). */
 int sift_b200_detect_u8(sift_b200_ctx* ctx, const uint8_t* pixels, int width, int height,

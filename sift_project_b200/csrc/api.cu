@@ -41,6 +41,7 @@ struct sift_b200_ctx {
     PyramidDesc* d_pyr = nullptr;
     Counters* d_counters = nullptr;
     Counters* h_counters = nullptr;  // pinned
+    float* d_range = nullptr;        // (min, max) of a float input
     Cand* d_cands = nullptr;
     KpCore* d_raw = nullptr;
     KpCore* d_oriented = nullptr;
@@ -258,6 +259,13 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     sp.dogs = dogs;
     sp.num_bins = (int)p.num_bins;
     sp.border = p.window_size / 2;
+    sp.mag_bound = 361.0;   // > sqrt(2) * 255
+    sp.range = nullptr;
+    if (sizeof(T) != 1) {   // float input: any range -- reduce it on the device
+        CU(c, launch_range((const float*)d_pixels, (size_t)width * height * channels, c->d_range, s));
+        sp.range = c->d_range;
+        c->launches += 1;
+    }
     sp.dog_threshold = (int)floor(0.5 * p.contrast_threshold / p.intervals * 255.0);  // sift.cpp:305-307
     sp.init_sigma = p.init_sigma;
     sp.contrast_threshold = p.contrast_threshold;
@@ -478,6 +486,7 @@ int sift_b200_create(int device, int max_width, int max_height, sift_b200_ctx** 
     CRT(cudaMalloc(&c->d_input, c->input_bytes));
     CRT(cudaMalloc(&c->d_pyr, sizeof(PyramidDesc)));
     CRT(cudaMalloc(&c->d_counters, sizeof(Counters)));
+    CRT(cudaMalloc(&c->d_range, 2 * sizeof(float)));
     CRT(cudaMallocHost(&c->h_counters, sizeof(Counters)));
     const size_t px = (size_t)max_width * max_height;
     c->cap_extrema = (int)std::max<size_t>(1 << 16, px / 2);
@@ -509,7 +518,7 @@ void sift_b200_destroy(sift_b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    void* ptrs[] = {c->arena, c->d_input, c->d_pyr, c->d_counters, c->d_cands, c->d_raw, c->d_oriented,
+    void* ptrs[] = {c->arena, c->d_input, c->d_pyr, c->d_counters, c->d_range, c->d_cands, c->d_raw, c->d_oriented,
                     c->d_records, c->d_desc, c->ss.bucket_cnt, c->ss.bucket_off, c->ss.bucket_fill,
                     c->ss.uniq_cnt, c->ss.uniq_off, c->ss.perm, c->ss.tmp_sorted, c->ss.sorted,
                     c->ss.final_order, c->ms.part_idx, c->ms.part_d1, c->ms.part_d2, c->ms.norms_a,

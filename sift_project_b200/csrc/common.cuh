@@ -68,6 +68,11 @@ struct StageParams {
     int dogs;                 // intervals + 2
     int num_bins;             // orientation histogram bins (declared double, used as int, sift.cpp:450)
     int border;               // window_size / 2 (sift.cpp:272, :336)
+    // Bound of the gradient magnitude for the fixed-point histograms: sqrt(2) * (max - min) of the
+    // input (blurs and the bilinear up-sampling stay inside the input's range).  8-bit input: 361
+    // on the host; float input: range[0..1] = (min, max), reduced on the device before the pyramid.
+    double mag_bound;
+    const float* range;
     int dog_threshold;        // floor(0.5*ct/intervals*255) squeezed into an int (sift.cpp:266,305)
     double init_sigma;
     double contrast_threshold;

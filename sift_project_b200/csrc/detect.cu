@@ -48,6 +48,34 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     return r;
 }
 
+// (min, max) of a float image, for the fixed-point histogram scale of float inputs.  Order-free
+// (min / max commute), so the result is reproducible.  range[] must hold (+inf, -inf) on entry.
+__device__ __forceinline__ void atomic_min_f(float* a, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int*>(a), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* a, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(a), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+__global__ void __launch_bounds__(256) k_range(const float* __restrict__ px, size_t n, float* __restrict__ range) {
+    float lo = INFINITY, hi = -INFINITY;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = __ldg(px + i);
+        lo = fminf(lo, v);
+        hi = fmaxf(hi, v);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+    if ((threadIdx.x & 31) == 0 && lo <= hi) {
+        atomic_min_f(range, lo);
+        atomic_max_f(range + 1, hi);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Extrema scan -- sift.cpp:264-291 (detect_octave_extrema) + :227-256 (is_extremum).
 // A pixel is kept iff |D| > threshold and it is >= all 26 neighbours or <= all of them (ties do
@@ -277,6 +305,8 @@ k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, Kp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* smooth = s_smooth[warp];
     const int n = min(counters->n_raw, sp.cap_raw);
+    const double mag_bound = sp.range ? fmax(1.4142135623730951 * ((double)sp.range[1] - (double)sp.range[0]), 1e-30) * 1.001
+                                      : sp.mag_bound;
     unsigned* hist = &s_hist[warp][0][0];
     unsigned* my_hist = s_hist[warp][lane & (COPIES - 1)];
     // keypoints cost 4x more or less than one another: warps pull the next one from a shared cursor
@@ -295,7 +325,7 @@ k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, Kp
         const int radius = (int)round(3.0 * scale);
         const float neg_inv_denom = (float)(-1.0 / (2.0 * scale * scale));
         const double g1 = 1.0 + 2.5066282746310002 * scale;
-        const double bound = g1 * g1 * 361.0;
+        const double bound = g1 * g1 * mag_bound;
         const float fix = (float)(4294967296.0 / bound);
         const double unfix = bound / 4294967296.0;
         const float bins_per_rad = (float)nb * (1.0f / 6.283185307179586f);
@@ -556,6 +586,8 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
     unsigned* hist = &s_hist[warp][0][0];
     unsigned* my_hist = s_hist[warp][lane & (DESC_COPIES - 1)];
     const int n = min(counters->n_final, cap_final);
+    const double mag_bound = sp.range ? fmax(1.4142135623730951 * ((double)sp.range[1] - (double)sp.range[0]), 1e-30) * 1.001
+                                      : sp.mag_bound;
     for (;;) {   // work stealing: the window area varies 4x between keypoints
         int i = 0;
         if (lane == 0) i = atomicAdd(&counters->next_describe, 1);
@@ -575,7 +607,7 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
         const float ca = (float)cos(kp.pori), sa = (float)sin(kp.pori);
         const float inv_hw = (float)(1.0 / hw);
         const float pori = (float)kp.pori;
-        const float fix = (float)(4294967296.0 / ((hw + 2.0) * (hw + 2.0) * 361.0));
+        const float fix = (float)(4294967296.0 / ((hw + 2.0) * (hw + 2.0) * mag_bound));
         for (int b = lane; b < DESC_COPIES * DESC_WORDS; b += 32) hist[b] = 0u;
         __syncwarp();
         // |col*sa + row*ca| < 2.5 hw  and  |col*ca - row*sa| < 2.5 hw  (bins in (-1, 4)), widened
@@ -713,6 +745,14 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
 }
 
 }  // namespace
+
+cudaError_t launch_range(const float* px, size_t n, float* range, cudaStream_t s) {
+    const float init[2] = {INFINITY, -INFINITY};
+    cudaError_t e = cudaMemcpyAsync(range, init, sizeof init, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+    k_range<<<148 * 4, 256, 0, s>>>(px, n, range);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int border, int threshold, Cand* cands,
                            int cap, Counters* counters, cudaStream_t s) {

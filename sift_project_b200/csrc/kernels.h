@@ -33,6 +33,7 @@ struct SortScratch {
     int* sorted;        // [cap_oriented]
     int* final_order;   // [cap_oriented]
 };
+cudaError_t launch_range(const float* px, size_t n, float* range, cudaStream_t s);
 cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int border, int threshold, Cand* cands,
                            int cap, Counters* counters, cudaStream_t s);
 cudaError_t launch_refine(const PyramidDesc* d_pyr, const Cand* cands, KpCore* raw,

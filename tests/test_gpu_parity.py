@@ -570,3 +570,19 @@ def test_window_and_bin_counts_vs_oracle(ctx, kw):
     assert len(want) > 30
     assert rec >= 0.99 and prec >= 0.99
     assert rep["frac_le1"] >= 0.98
+
+
+@pytest.mark.parametrize("scale,offset", [(100.0, 0.0), (0.01, -1.0), (1.0, -128.0)])
+def test_float_input_of_any_range(ctx, scale, offset):
+    """sift_b200_detect_f32 on data far outside 0..255 (and negative): the fixed-point histogram
+    scale follows the input's own range, so nothing overflows or underflows."""
+    img = O.synth_image(240, 320, seed=41).astype(np.float32) * np.float32(scale) + np.float32(offset)
+    kw = dict(contrast_threshold=0.04 * scale) if scale < 1 else {}
+    got = ctx.detect(img, **kw)
+    want = O.Run(O.best(), img.astype(np.float64), params=O.Params(**kw), keep_pyramid=False).keypoints(2)
+    rec, prec, gi, wi = P.recall_precision(got, want)
+    rep = P.descriptor_report(got, want, gi, wi)
+    REPORT[f"f32_range_x{scale}_{offset}"] = dict(n_gpu=len(got), n_ref=len(want), recall=rec, precision=prec, desc=rep)
+    assert len(want) > 50
+    assert rec >= 0.99 and prec >= 0.99
+    assert rep["frac_le1"] >= 0.97
