@@ -10,7 +10,7 @@
 #ifdef V2
 #define LAUNCH(a1,a2,a3) launch_cascade_t<a1,a2,a3>(a, 148, 0)
 #else
-#define LAUNCH(a1,a2,a3) launch_cascade_t<a1,a2,a3>(a, 0)
+#define LAUNCH(a1,a2,a3) launch_cascade_t<a1,a2,a3>(a, 148, 0)
 #endif
 namespace sb {
 static BlurTaps mk(double sigma) {

@@ -332,7 +332,7 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
                 OctaveDesc& nx = c->pyr.oct[o + 1];
                 dec = nx.G[0]; dw = nx.w; dh = nx.h; dp = nx.pitch;
             }
-            CU(c, launch_octave_fused(od, taps, dec, dw, dh, dp, c->keep_planes, s));
+            CU(c, launch_octave_fused(od, taps, dec, dw, dh, dp, c->keep_planes, c->sm_count, s));
             prof_mark(c, SIFT_B200_STAGE_PYRAMID, 2);
         } else {
         for (int i = 1; i < layers; ++i) {

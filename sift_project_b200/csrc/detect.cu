@@ -762,12 +762,15 @@ cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int bord
         k_extrema_window<<<grid, 256, 0, s>>>(oct, octave, dogs, border, (float)threshold, cands, cap, counters);
         return cudaGetLastError();
     }
-    const bool big = (long long)oct.w * oct.h >= (16ll << 20);
-    dim3 grid((oct.w - 2 + 29) / 30, (oct.h - 2 + 8 * (big ? 32 : 8) - 1) / (8 * (big ? 32 : 8)));
-#define SB_EX(ND)                                                                                            \
-    case ND:                                                                                                 \
-        if (big) k_extrema<32, ND><<<grid, 256, 0, s>>>(oct, octave, (float)threshold, cands, cap, counters); \
-        else k_extrema<8, ND><<<grid, 256, 0, s>>>(oct, octave, (float)threshold, cands, cap, counters);      \
+    // rows per warp: 32 on large octaves, 8 on mid-size ones, 2 on tiny ones (more warps, shorter serial walks)
+    const long long px = (long long)oct.w * oct.h;
+    const int rows = px >= (16ll << 20) ? 32 : px >= (1ll << 18) ? 8 : 2;
+    dim3 grid((oct.w - 2 + 29) / 30, (oct.h - 2 + 8 * rows - 1) / (8 * rows));
+#define SB_EX(ND)                                                                                                  \
+    case ND:                                                                                                       \
+        if (rows == 32) k_extrema<32, ND><<<grid, 256, 0, s>>>(oct, octave, (float)threshold, cands, cap, counters); \
+        else if (rows == 8) k_extrema<8, ND><<<grid, 256, 0, s>>>(oct, octave, (float)threshold, cands, cap, counters); \
+        else k_extrema<2, ND><<<grid, 256, 0, s>>>(oct, octave, (float)threshold, cands, cap, counters);            \
         break;
     switch (dogs) {
         SB_EX(4) SB_EX(5) SB_EX(6) SB_EX(7)

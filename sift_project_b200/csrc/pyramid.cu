@@ -159,15 +159,15 @@ constexpr int CTW = 64;  // cascade tile width: 64 x 64 tiles need ~110 KB, so T
 __host__ __device__ constexpr int ru4(int v) { return (v + 3) & ~3; }
 __host__ __device__ constexpr int ru2(int v) { return (v + 1) & ~1; }
 
-template <int R1, int R2, int R3>
+template <int R1, int R2, int R3, int TWP, int THP>
 struct CascadeGeom {
     static constexpr int NL = R3 > 0 ? 3 : 2;
     static constexpr int HX2 = NL == 3 ? ru4(R3) : 0, HY2 = NL == 3 ? ru2(R3) : 0;  // halo kept around level 2
     static constexpr int HX1 = ru4(HX2 + R2), HY1 = ru2(HY2 + R2);                  // ... around level 1
     static constexpr int HX0 = ru4(HX1 + R1), HY0 = ru2(HY1 + R1);                  // ... around the input
-    static constexpr int W0 = CTW + 2 * HX0, H0 = TH + 2 * HY0;
-    static constexpr int W1 = CTW + 2 * HX1, H1 = TH + 2 * HY1;
-    static constexpr int W2 = CTW + 2 * HX2, H2 = TH + 2 * HY2;
+    static constexpr int W0 = TWP + 2 * HX0, H0 = THP + 2 * HY0;
+    static constexpr int W1 = TWP + 2 * HX1, H1 = THP + 2 * HY1;
+    static constexpr int W2 = TWP + 2 * HX2, H2 = THP + 2 * HY2;
     static constexpr int A_FLOATS = W0 * H0;   // input, later level 2
     static constexpr int T_FLOATS = W1 * H0;   // horizontal-pass scratch (largest: level 1)
     static constexpr int B_FLOATS = W1 * H1;   // level 1
@@ -274,9 +274,11 @@ __device__ unsigned long long g_phase[16];
 #define SB_PHASE_INIT
 #endif
 
-template <int R1, int R2, int R3>
-__global__ void __launch_bounds__(CCT, 2) k_cascade(const CascadeArgs a) {
-    using G = CascadeGeom<R1, R2, R3>;
+// TWP x THP = tile, NTP = threads, MINB = CTAs per SM.  64 x 64 / 384 / 2 for large octaves; 32 x 32 / 128 / 4
+// for octaves that would not fill the GPU with 64 x 64 tiles (a lone CTA takes 10-18 us per tile).
+template <int R1, int R2, int R3, int TWP, int THP, int NTP, int MINB>
+__global__ void __launch_bounds__(NTP, MINB) k_cascade(const CascadeArgs a) {
+    using G = CascadeGeom<R1, R2, R3, TWP, THP>;
     SB_PHASE_INIT
     extern __shared__ __align__(16) float smem[];
     float* sA = smem;
@@ -284,20 +286,20 @@ __global__ void __launch_bounds__(CCT, 2) k_cascade(const CascadeArgs a) {
     float* sB = sT + G::T_FLOATS;
     const int tid = threadIdx.x;
     const int w = a.w, h = a.h, pitch = a.pitch;
-    const int tx0 = blockIdx.x * CTW, ty0 = blockIdx.y * TH;
+    const int tx0 = blockIdx.x * TWP, ty0 = blockIdx.y * THP;
     const int gx0 = tx0 - G::HX0, gy0 = ty0 - G::HY0;
-    const bool interior = gx0 >= 0 && gy0 >= 0 && (tx0 + CTW + G::HX0) <= w && (ty0 + TH + G::HY0) <= h;
+    const bool interior = gx0 >= 0 && gy0 >= 0 && (tx0 + TWP + G::HX0) <= w && (ty0 + THP + G::HY0) <= h;
 
     // ---- stage the input tile (replicate padding == the reference's index clamping) ----
     if (interior) {
         constexpr int V = G::W0 / 4;
-        for (int idx = tid; idx < G::H0 * V; idx += CCT) {
+        for (int idx = tid; idx < G::H0 * V; idx += NTP) {
             const int r = idx / V, c4 = idx - r * V;
             cp_async16(sA + r * G::W0 + 4 * c4, a.in + (size_t)(gy0 + r) * pitch + gx0 + 4 * c4);
         }
         cp_async_wait_all();
     } else {
-        for (int idx = tid; idx < G::H0 * G::W0; idx += CCT) {
+        for (int idx = tid; idx < G::H0 * G::W0; idx += NTP) {
             const int r = idx / G::W0, c = idx - r * G::W0;
             const int gy = min(max(gy0 + r, 0), h - 1), gx = min(max(gx0 + c, 0), w - 1);
             sA[idx] = __ldg(a.in + (size_t)gy * pitch + gx);
@@ -333,10 +335,10 @@ __global__ void __launch_bounds__(CCT, 2) k_cascade(const CascadeArgs a) {
     };
 
     // ---- level 1: sA -> sT -> sB ----
-    cascade_hpass<CCT, R1, G::W0, G::W1, G::HX0 - G::HX1>(sA, sT, G::H0, a.taps[0]);
+    cascade_hpass<NTP, R1, G::W0, G::W1, G::HX0 - G::HX1>(sA, sT, G::H0, a.taps[0]);
     __syncthreads();
     SB_PHASE(1);
-    cascade_vpass<CCT, R1, G::W1>(sT + (G::HY0 - G::HY1 - R1) * G::W1, G::H1, a.taps[0],
+    cascade_vpass<NTP, R1, G::W1>(sT + (G::HY0 - G::HY1 - R1) * G::W1, G::H1, a.taps[0],
                              [&](int y, int q, const float4 (&acc)[4]) {
 #pragma unroll
                                  for (int k = 0; k < 4; ++k)
@@ -345,8 +347,8 @@ __global__ void __launch_bounds__(CCT, 2) k_cascade(const CascadeArgs a) {
     __syncthreads();
     SB_PHASE(2);
     // emit the centre of level 1 (+ DoG against the input centre)
-    for (int idx = tid; idx < (TH / 4) * (CTW / 4); idx += CCT) {
-        const int g = idx / (CTW / 4), q = idx - g * (CTW / 4);
+    for (int idx = tid; idx < (THP / 4) * (TWP / 4); idx += NTP) {
+        const int g = idx / (TWP / 4), q = idx - g * (TWP / 4);
         float4 acc[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -356,17 +358,17 @@ __global__ void __launch_bounds__(CCT, 2) k_cascade(const CascadeArgs a) {
     // interior tiles go straight on: the next pass only reads what the emission reads
     if (!interior) {
         __syncthreads();
-        cascade_fix_edges<CCT, G::W1, G::H1>(sB, tx0 - G::HX1, ty0 - G::HY1, w, h);
+        cascade_fix_edges<NTP, G::W1, G::H1>(sB, tx0 - G::HX1, ty0 - G::HY1, w, h);
         __syncthreads();
     }
     SB_PHASE(4);
 
     if (G::NL == 3) {
         // ---- level 2: sB -> sT -> sA (the input is dead by now) ----
-        cascade_hpass<CCT, R2, G::W1, G::W2, G::HX1 - G::HX2>(sB, sT, G::H1, a.taps[1]);
+        cascade_hpass<NTP, R2, G::W1, G::W2, G::HX1 - G::HX2>(sB, sT, G::H1, a.taps[1]);
         __syncthreads();
     SB_PHASE(5);
-        cascade_vpass<CCT, R2, G::W2>(sT + (G::HY1 - G::HY2 - R2) * G::W2, G::H2, a.taps[1],
+        cascade_vpass<NTP, R2, G::W2>(sT + (G::HY1 - G::HY2 - R2) * G::W2, G::H2, a.taps[1],
                                  [&](int y, int q, const float4 (&acc)[4]) {
 #pragma unroll
                                      for (int k = 0; k < 4; ++k)
@@ -374,8 +376,8 @@ __global__ void __launch_bounds__(CCT, 2) k_cascade(const CascadeArgs a) {
                                  });
         __syncthreads();
     SB_PHASE(6);
-        for (int idx = tid; idx < (TH / 4) * (CTW / 4); idx += CCT) {
-            const int g = idx / (CTW / 4), q = idx - g * (CTW / 4);
+        for (int idx = tid; idx < (THP / 4) * (TWP / 4); idx += NTP) {
+            const int g = idx / (TWP / 4), q = idx - g * (TWP / 4);
             float4 acc[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -384,24 +386,24 @@ __global__ void __launch_bounds__(CCT, 2) k_cascade(const CascadeArgs a) {
         }
         if (!interior) {
             __syncthreads();
-            cascade_fix_edges<CCT, G::W2, G::H2>(sA, tx0 - G::HX2, ty0 - G::HY2, w, h);
+            cascade_fix_edges<NTP, G::W2, G::H2>(sA, tx0 - G::HX2, ty0 - G::HY2, w, h);
             __syncthreads();
         }
     SB_PHASE(8);
         // ---- level 3: sA -> sT -> registers -> HBM ----
-        cascade_hpass<CCT, (R3 > 0 ? R3 : 1), G::W2, CTW, G::HX2>(sA, sT, G::H2, a.taps[2]);
+        cascade_hpass<NTP, (R3 > 0 ? R3 : 1), G::W2, TWP, G::HX2>(sA, sT, G::H2, a.taps[2]);
         __syncthreads();
     SB_PHASE(9);
-        cascade_vpass<CCT, (R3 > 0 ? R3 : 1), CTW>(sT + (G::HY2 - R3) * CTW, TH, a.taps[2],
+        cascade_vpass<NTP, (R3 > 0 ? R3 : 1), TWP>(sT + (G::HY2 - R3) * TWP, THP, a.taps[2],
                                            [&](int y, int q, const float4 (&acc)[4]) {
                                                store_level(a.g[2], a.d[2], sA, G::W2, G::HX2, G::HY2, y, q, acc, true);
                                            });
     } else {
         // ---- two-level variant: level 2 is the last: sB -> sT -> registers -> HBM ----
-        cascade_hpass<CCT, R2, G::W1, CTW, G::HX1>(sB, sT, G::H1, a.taps[1]);
+        cascade_hpass<NTP, R2, G::W1, TWP, G::HX1>(sB, sT, G::H1, a.taps[1]);
         __syncthreads();
     SB_PHASE(10);
-        cascade_vpass<CCT, R2, CTW>(sT + (G::HY1 - R2) * CTW, TH, a.taps[1],
+        cascade_vpass<NTP, R2, TWP>(sT + (G::HY1 - R2) * TWP, THP, a.taps[1],
                               [&](int y, int q, const float4 (&acc)[4]) {
                                   store_level(a.g[1], a.d[1], sB, G::W1, G::HX1, G::HY1, y, q, acc, true);
                               });
@@ -410,9 +412,15 @@ __global__ void __launch_bounds__(CCT, 2) k_cascade(const CascadeArgs a) {
 }
 
 template <int R1, int R2, int R3>
-cudaError_t launch_cascade_t(const CascadeArgs& a, cudaStream_t s) {
-    dim3 grid((a.w + CTW - 1) / CTW, (a.h + TH - 1) / TH);
-    k_cascade<R1, R2, R3><<<grid, CCT, CascadeGeom<R1, R2, R3>::kSmem, s>>>(a);
+cudaError_t launch_cascade_t(const CascadeArgs& a, int sm_count, cudaStream_t s) {
+    const int big_tiles = ((a.w + CTW - 1) / CTW) * ((a.h + TH - 1) / TH);
+    if (big_tiles >= 2 * sm_count) {
+        dim3 grid((a.w + CTW - 1) / CTW, (a.h + TH - 1) / TH);
+        k_cascade<R1, R2, R3, CTW, TH, CCT, 2><<<grid, CCT, CascadeGeom<R1, R2, R3, CTW, TH>::kSmem, s>>>(a);
+    } else {
+        dim3 grid((a.w + 31) / 32, (a.h + 31) / 32);
+        k_cascade<R1, R2, R3, 32, 32, 128, 4><<<grid, 128, CascadeGeom<R1, R2, R3, 32, 32>::kSmem, s>>>(a);
+    }
     return cudaGetLastError();
 }
 
@@ -555,10 +563,13 @@ cudaError_t pyramid_init() {
                                   (int)kInputSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_input_u8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)kInputSmem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_cascade<4, 5, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)CascadeGeom<4, 5, 6>::kSmem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_cascade<8, 10, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)CascadeGeom<8, 10, 0>::kSmem)) != cudaSuccess) return e;
+#define SB_CASC_ATTR(R1, R2, R3, TWP, THP, NTP, MINB)                                                       \
+    if ((e = cudaFuncSetAttribute(k_cascade<R1, R2, R3, TWP, THP, NTP, MINB>,                             \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
+                                  (int)CascadeGeom<R1, R2, R3, TWP, THP>::kSmem)) != cudaSuccess) return e;
+    SB_CASC_ATTR(4, 5, 6, CTW, TH, CCT, 2) SB_CASC_ATTR(8, 10, 0, CTW, TH, CCT, 2)
+    SB_CASC_ATTR(4, 5, 6, 32, 32, 128, 4) SB_CASC_ATTR(8, 10, 0, 32, 32, 128, 4)
+#undef SB_CASC_ATTR
 #define SB_INIT(R) if ((e = init_blur_r<R>()) != cudaSuccess) return e;
     SB_INIT(1) SB_INIT(2) SB_INIT(3) SB_INIT(4) SB_INIT(5) SB_INIT(6) SB_INIT(7) SB_INIT(8)
     SB_INIT(9) SB_INIT(10) SB_INIT(11) SB_INIT(12) SB_INIT(13) SB_INIT(14) SB_INIT(15) SB_INIT(16)
@@ -599,7 +610,7 @@ bool cascade_supported(const BlurTaps* taps) {
 
 // One octave: G[0] -> G[1..3], D[0..4], next base.  keep_all also stores G[4], G[5] (debug planes).
 cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, float* dec, int dec_w, int dec_h,
-                                int dec_pitch, bool keep_all, cudaStream_t s) {
+                                int dec_pitch, bool keep_all, int sm_count, cudaStream_t s) {
     CascadeArgs a;
     a.in = od.G[0];
     a.g[0] = od.G[1]; a.g[1] = od.G[2]; a.g[2] = od.G[3];
@@ -607,7 +618,7 @@ cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, floa
     a.dec = dec; a.dec_w = dec_w; a.dec_h = dec_h; a.dec_pitch = dec_pitch;
     a.w = od.w; a.h = od.h; a.pitch = od.pitch;
     a.taps[0] = taps[1]; a.taps[1] = taps[2]; a.taps[2] = taps[3];
-    cudaError_t e = launch_cascade_t<4, 5, 6>(a, s);
+    cudaError_t e = launch_cascade_t<4, 5, 6>(a, sm_count, s);
     if (e != cudaSuccess) return e;
     CascadeArgs b;
     b.in = od.G[3];
@@ -616,7 +627,7 @@ cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, floa
     b.dec = nullptr; b.dec_w = b.dec_h = b.dec_pitch = 0;
     b.w = od.w; b.h = od.h; b.pitch = od.pitch;
     b.taps[0] = taps[4]; b.taps[1] = taps[5]; b.taps[2] = taps[5];
-    return launch_cascade_t<8, 10, 0>(b, s);
+    return launch_cascade_t<8, 10, 0>(b, sm_count, s);
 }
 
 cudaError_t launch_prepare_u8(const uint8_t* src, int sw, int sh, int ch, float* dst, int dw, int dh,
