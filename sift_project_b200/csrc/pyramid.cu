@@ -424,6 +424,8 @@ cudaError_t launch_cascade_t(const CascadeArgs& a, int sm_count, cudaStream_t s)
     return cudaGetLastError();
 }
 
+#include "stream.cuh"
+
 // ------------------------------------------------------------------------------------------
 // Fused input stage for 8-bit gray images: resize_inter_bilinear(2,2) (image.cpp:62-88, optional)
 // + the initial blur (sift.cpp:124, radius 4) in one pass: the up-sampled tile is formed in shared
@@ -570,6 +572,10 @@ cudaError_t pyramid_init() {
     SB_CASC_ATTR(4, 5, 6, CTW, TH, CCT, 2) SB_CASC_ATTR(8, 10, 0, CTW, TH, CCT, 2)
     SB_CASC_ATTR(4, 5, 6, 32, 32, 128, 4) SB_CASC_ATTR(8, 10, 0, 32, 32, 128, 4)
 #undef SB_CASC_ATTR
+    if ((e = cudaFuncSetAttribute(k_stream<StreamA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)StreamA::kSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_stream<StreamB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)StreamB::kSmem)) != cudaSuccess) return e;
 #define SB_INIT(R) if ((e = init_blur_r<R>()) != cudaSuccess) return e;
     SB_INIT(1) SB_INIT(2) SB_INIT(3) SB_INIT(4) SB_INIT(5) SB_INIT(6) SB_INIT(7) SB_INIT(8)
     SB_INIT(9) SB_INIT(10) SB_INIT(11) SB_INIT(12) SB_INIT(13) SB_INIT(14) SB_INIT(15) SB_INIT(16)

@@ -1,0 +1,371 @@
+// Streaming (rolling column-strip) form of the fused Gaussian cascade (sm_100a).  Included by pyramid.cu
+// inside its anonymous namespace (uses CascadeArgs, BlurTaps, cp_async16, ru4).
+//
+// Same arithmetic as k_cascade / k_blur (image.cpp:156-238 per level, subtract image.cpp:30-36, nearest
+// decimation image.cpp:41-55), bit-identical results, different data movement:
+//
+//   * a CTA owns a column strip of WS outputs and a segment of rows and walks DOWN the rows, one row per
+//     step; there is no y halo to recompute (only a warm-up of sum(R) rows per segment) and no 2-D tile
+//     passing through shared memory in barrier-separated passes;
+//   * the levels of the cascade form a pipeline over shared-memory row rings: the warps of level l read
+//     the row that level l-1 completed in the previous step, so one CTA barrier per row step is enough;
+//   * per step a thread of level l (C adjacent columns) runs the horizontal pass of ONE row from a
+//     register window (C + 2R floats, vector LDS) and then the vertical pass in SCATTER form: the new
+//     horizontal value is accumulated into the 2R+1 output rows it contributes to, which live in
+//     registers ((2R+1) x C rotating accumulators, rotation resolved at compile time by unrolling the
+//     step loop 2R+1 times).  Each accumulator receives its terms in ascending input-row order starting
+//     from fma(w[R], v, 0) -- exactly the order of cascade_vpass -- so the sums round identically;
+//   * the row that completes is written to the level's ring (next level's input) and, inside the
+//     strip, straight from registers to HBM together with its DoG against the previous level's row.
+//
+// Shared-memory traffic per pixel and level drops from ~(2 + R) floats to ~(2 + R/4); HBM traffic is the
+// same 4 + 24 (+1) and 4 + 8 bytes per octave pixel as the tile kernels.
+//
+// Clamp-to-edge semantics of every level: rows outside the image are read as the edge row of the ring
+// (virtual row index clamped); columns outside the image are read with clamped column indices in the
+// strips that touch the left / right image edge (BORDER variant of the window load).
+
+struct StreamSched {
+    int y0, y1;            // output rows [y0, y1) of the last level
+    int r0, rlast;         // input rows the strip segment needs
+    int T[4], Tend[4];     // level l is active for steps T[l] .. Tend[l]
+    int i0[4];             // virtual input row of level l at step T[l] (may be negative: replicated row 0)
+    int f[4], e[4];        // first / last row of level l that is needed (f[0], e[0] = r0, rlast)
+    int steps;
+};
+
+template <int NL_, int R1_, int R2_, int R3_, int C_, int WS_, int PF_, int MINB_, bool PACK_>
+struct StreamGeom {
+    static constexpr int NL = NL_, C = C_, WS = WS_, PF = PF_, MINB = MINB_;
+    static constexpr bool PACK = PACK_;
+    __host__ __device__ static constexpr int R(int l) { return l == 1 ? R1_ : l == 2 ? R2_ : l == 3 ? R3_ : 0; }
+    __host__ __device__ static constexpr int RA(int l) { return ru4(R(l)); }
+    // x halo kept around level l (columns computed beyond the strip so that the later levels have their windows)
+    __host__ __device__ static constexpr int HO(int l) { return l >= NL ? 0 : HO(l + 1) + RA(l + 1); }
+    __host__ __device__ static constexpr int W(int l) { return WS + 2 * HO(l); }
+    __host__ __device__ static constexpr int NTH(int l) { return W(l) / C; }
+    __host__ __device__ static constexpr int WARPS(int l) { return l < 1 || l > NL ? 0 : (NTH(l) + 31) / 32; }
+    __host__ __device__ static constexpr int FIRSTWARP(int l) { return l <= 1 ? 0 : FIRSTWARP(l - 1) + WARPS(l - 1); }
+    static constexpr int THREADS = 32 * (FIRSTWARP(NL) + WARPS(NL));
+    // ring depths: see the schedule in k_stream
+    __host__ __device__ static constexpr int DEPTH(int l) { return l == 0 ? PF + 2 * R(1) + 2 : 2 * R(l + 1) + 2; }
+    __host__ __device__ static constexpr int OFF(int l) { return l <= 0 ? 0 : OFF(l - 1) + DEPTH(l - 1) * W(l - 1); }
+    static constexpr size_t kSmem = (size_t)OFF(NL) * sizeof(float);
+    static_assert(WS % C == 0 && C % 4 == 0, "strip width / columns per thread");
+};
+
+__device__ __forceinline__ void stream_bar() {
+#ifndef SB_EXP_NOBAR
+    asm volatile("bar.sync 0;\n" ::: "memory");
+#endif
+}
+
+template <int N>
+__device__ __forceinline__ void stream_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// Input rows are fetched by the warps of level 1 (the lightest level): cp.async of one 16-byte chunk per lane
+// (+ a second one for the first few lanes), PF rows ahead; one commit group per step.
+template <class G>
+struct StreamFetch {
+    static constexpr int W0 = G::W(0), D0 = G::DEPTH(0), NT = 32 * G::WARPS(1), CH = W0 / 4;
+    static constexpr int PER = (CH + NT - 1) / NT;
+    const float* src;     // next row to fetch, at this thread's first chunk
+    unsigned dst;         // shared-memory byte address of that chunk in the ring slot of the next row
+    unsigned dst_end;     // ring end (byte address, at this thread's first chunk)
+    int rows_left;
+    size_t pitch;
+    bool ok[PER];
+
+    __device__ __forceinline__ void init(const CascadeArgs& a, float* smem, int rt, int r0, int rlast, int sx0) {
+        const int gx = sx0 - G::HO(0) + 4 * rt;
+        src = a.in + (size_t)r0 * a.pitch + gx;
+        pitch = a.pitch;
+        const unsigned base = (unsigned)__cvta_generic_to_shared(smem) + 16u * rt;
+        dst = base + (unsigned)((r0 % D0) * W0 * 4);
+        dst_end = base + (unsigned)(D0 * W0 * 4);
+        rows_left = rlast - r0 + 1;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int c = rt + k * NT, x = gx + 4 * k * NT;
+            ok[k] = c < CH && x >= 0 && x < a.pitch;
+        }
+    }
+    __device__ __forceinline__ void next() {
+        if (rows_left > 0) {
+#pragma unroll
+            for (int k = 0; k < PER; ++k)
+                if (ok[k])
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 16u * k * NT),
+                                 "l"(src + 4 * k * NT));
+            src += pitch;
+            dst += W0 * 4;
+            if (dst == dst_end) dst -= D0 * W0 * 4;
+            --rows_left;
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    }
+};
+
+// One level of the pipeline, run by the warps of that level.  rt = thread index inside the level.
+// Everything that moves with the row (ring slots, plane offsets) is a running counter: no division, no
+// 64-bit multiply inside the step.
+template <class G, int L, bool BORDER>
+__device__ __forceinline__ void stream_level(const CascadeArgs& a, float* smem, const int rt,
+                                             const StreamSched& sc, const int sx0) {
+    constexpr int R = G::R(L), RA = G::RA(L), C = G::C, C2 = C / 2;
+    constexpr int WP = G::W(L - 1), DP = G::DEPTH(L - 1);
+    constexpr int WL = G::W(L), DL = L < G::NL ? G::DEPTH(L) : 1;
+    constexpr bool LAST = L == G::NL;
+    const float* ringP = smem + G::OFF(L - 1);
+    float* ringL = smem + (LAST ? 0 : G::OFF(L));
+    const BlurTaps& tp = a.taps[L - 1];
+    const int w = a.w, h = a.h;
+
+    const bool dup = rt >= G::NTH(L);                     // spare lanes of the last warp repeat the last thread
+    const int x = (dup ? G::NTH(L) - 1 : rt) * C;         // first column inside the level's region
+    const int gx = sx0 - G::HO(L) + x;                    // ... in the image
+    const bool store_ok = !dup && x >= G::HO(L) && x < G::HO(L) + G::WS && gx < w;
+    // BORDER: clamp window columns to the image (ring column of image column 0 / w-1)
+    const int clo = max(0, -(sx0 - G::HO(L - 1)));
+    const int chi = min(WP - 1, w - 1 - (sx0 - G::HO(L - 1)));
+
+    float* gout = a.g[L - 1];
+    float* dout = a.d[L - 1];
+    float* decp = LAST ? a.dec : nullptr;
+
+    // acc[p] = partial sum of output row (i - R + 1 + p) after input row i: 2R rows are in flight
+    float2 acc[2 * R][C2];
+#pragma unroll
+    for (int p = 0; p < 2 * R; ++p)
+#pragma unroll
+        for (int c = 0; c < C2; ++c) acc[p][c] = make_float2(0.f, 0.f);
+    float2 w2[R + 1];
+#pragma unroll
+    for (int d = 0; d <= R; ++d) w2[d] = make_float2(tp.w[d], tp.w[d]);
+
+    const int T = sc.T[L], Tend = sc.Tend[L], steps = sc.steps;
+    const int fL = sc.f[L], eL = sc.e[L];
+    const int i0 = sc.i0[L];
+    auto mod = [](int v, int m) { return ((v % m) + m) % m; };
+    // running state of the step loop
+    int i = i0;                                            // virtual input row
+    int in_off = (min(max(i0, 0), h - 1) % DP) * WP;       // ring slot (floats) of the clamped input row
+    int cen_off = mod(i0 - R, DP) * WP;                    // ... of the previous level's row y (DoG centre)
+    int out_off = mod(i0 - R, DL) * WL;                    // ... of this level's row y
+    unsigned e_off = (unsigned)((long long)(i0 - R) * a.pitch + gx);   // plane offset of (y, gx); wraps while y < 0
+
+    StreamFetch<G> fetch;
+    if (L == 1) {
+        fetch.init(a, smem, rt, sc.r0, sc.rlast, sx0);
+#pragma unroll 1
+        for (int g = 0; g < G::PF; ++g) fetch.next();
+    }
+
+#pragma unroll 1
+    for (int t = 0; t < steps; ++t) {
+        if (L == 1) {
+            fetch.next();
+            stream_wait<G::PF>();
+        }
+        stream_bar();
+        if (t < T || t > Tend) continue;   // pipeline fill / drain: this level has nothing to do
+        const float* rowp = ringP + in_off;
+        // ---- horizontal pass of one row: C outputs from a register window ----
+        float v[C + 2 * RA];
+        if (!BORDER) {
+            const float4* src = reinterpret_cast<const float4*>(rowp + x);
+#pragma unroll
+            for (int k = 0; k < (C + 2 * RA) / 4; ++k) {
+                if (4 * k + 3 < RA - R || 4 * k >= RA + C + R) continue;   // outside the taps
+                const float4 q = src[k];
+                v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = RA - R; k < RA + C + R; ++k) v[k] = rowp[min(max(x + k, clo), chi)];
+        }
+        float2 hv[C2];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float sacc = 0.f;
+#pragma unroll
+            for (int u = R; u >= 1; --u) sacc = fmaf(tp.w[u], v[RA + c - u] + v[RA + c + u], sacc);
+            const float o = fmaf(tp.w[0], v[RA + c], sacc);
+            if (c & 1) hv[c / 2].y = o; else hv[c / 2].x = o;
+        }
+        // ---- vertical pass, scatter form: row i adds w[|i - y|] * h to every output row y in [i-R, i+R].  The
+        // accumulators move down one slot per step THROUGH the FMA (d = a * b + c with c = slot p+1, d = slot p):
+        // the rotation costs nothing, every index is static, and each row still receives its terms in ascending
+        // input-row order starting from fma(w[R], h, 0) ----
+        float2 out[C2];
+#pragma unroll
+        for (int c = 0; c < C2; ++c) {
+            if (G::PACK) {
+                out[c] = __ffma2_rn(w2[R], hv[c], acc[0][c]);
+            } else {
+                out[c].x = fmaf(tp.w[R], hv[c].x, acc[0][c].x);
+                out[c].y = fmaf(tp.w[R], hv[c].y, acc[0][c].y);
+            }
+        }
+#ifdef SB_EXP_NOV
+        if (hv[0].x == 123.456f)
+#endif
+#pragma unroll
+        for (int p = 0; p < 2 * R; ++p) {
+            const int d = R - 1 - p < 0 ? p + 1 - R : R - 1 - p;
+#pragma unroll
+            for (int c = 0; c < C2; ++c) {
+                const float2 prev = p + 1 < 2 * R ? acc[p + 1][c] : make_float2(0.f, 0.f);
+                if (G::PACK) {
+                    acc[p][c] = __ffma2_rn(w2[d], hv[c], prev);
+                } else {
+                    acc[p][c].x = fmaf(tp.w[d], hv[c].x, prev.x);
+                    acc[p][c].y = fmaf(tp.w[d], hv[c].y, prev.y);
+                }
+            }
+        }
+        // ---- the row that just received its last term ----
+        const int y = i - R;
+        if (y >= fL && y <= eL) {
+            if (!LAST) {
+                float4* dst = reinterpret_cast<float4*>(ringL + out_off + x);
+#pragma unroll
+                for (int k = 0; k < C / 4; ++k)
+                    dst[k] = make_float4(out[2 * k].x, out[2 * k].y, out[2 * k + 1].x, out[2 * k + 1].y);
+            }
+            if (store_ok && y >= sc.y0 && y < sc.y1) {
+                const float4* cen = reinterpret_cast<const float4*>(ringP + cen_off + x + RA);
+#pragma unroll
+                for (int k = 0; k < C / 4; ++k) {
+                    if (gx + 4 * k >= w) break;
+                    const float4 ov = make_float4(out[2 * k].x, out[2 * k].y, out[2 * k + 1].x, out[2 * k + 1].y);
+#ifdef SB_EXP_NOSTG
+                    if (ov.x == 123.456f)
+#endif
+                    if (gout != nullptr) *reinterpret_cast<float4*>(gout + e_off + 4 * k) = ov;
+                    if (dout != nullptr) {
+                        const float4 cv = cen[k];
+#ifdef SB_EXP_NOSTG
+                        if (cv.x == 123.456f)
+#endif
+                        *reinterpret_cast<float4*>(dout + e_off + 4 * k) =
+                            make_float4(ov.x - cv.x, ov.y - cv.y, ov.z - cv.z, ov.w - cv.w);
+                    }
+                    if (LAST && decp != nullptr && !(y & 1)) {
+                        const int dy = y >> 1, dx = (gx + 4 * k) >> 1;
+                        if (dy < a.dec_h) {
+                            if (dx + 1 < a.dec_w)
+                                *reinterpret_cast<float2*>(decp + (size_t)dy * a.dec_pitch + dx) =
+                                    make_float2(ov.x, ov.z);
+                            else if (dx < a.dec_w)
+                                decp[(size_t)dy * a.dec_pitch + dx] = ov.x;
+                        }
+                    }
+                }
+            }
+        }
+        // ---- advance the running state ----
+        if ((unsigned)i < (unsigned)(h - 1)) {   // rows above / below the image re-read the edge row
+            in_off += WP;
+            if (in_off == DP * WP) in_off = 0;
+        }
+        ++i;
+        cen_off += WP;
+        if (cen_off == DP * WP) cen_off = 0;
+        if (!LAST) {
+            out_off += WL;
+            if (out_off == DL * WL) out_off = 0;
+        }
+        e_off += (unsigned)a.pitch;
+    }
+}
+
+template <class G, bool BORDER>
+__device__ __forceinline__ void stream_body(const CascadeArgs& a, float* smem,
+                                            const StreamSched& sc, int sx0) {
+    const int warp = threadIdx.x >> 5;
+    if (G::NL >= 3 && warp >= G::FIRSTWARP(3))
+        stream_level<G, (G::NL >= 3 ? 3 : 1), BORDER>(a, smem, threadIdx.x - 32 * G::FIRSTWARP(3), sc, sx0);
+    else if (warp >= G::FIRSTWARP(2))
+        stream_level<G, 2, BORDER>(a, smem, threadIdx.x - 32 * G::FIRSTWARP(2), sc, sx0);
+    else
+        stream_level<G, 1, BORDER>(a, smem, threadIdx.x, sc, sx0);
+}
+
+// Schedule (per CTA, uniform).  Level l consumes virtual input row i_l(t) = i0[l] + (t - T[l]) at step t and
+// completes its row i_l(t) - R_l in the same step.  Level l starts the step after level l-1 completed the
+// first row level l reads, so from then on the row it needs was always completed one step earlier.  At the
+// top of the image i0[l] = -R_l: the level re-reads ring row 0 for R_l steps while its producer runs ahead,
+// hence ring depth 2 R_l + 2 (window row .. centre row of the DoG .. row being written); the input ring adds
+// the prefetch distance.
+// Work split: the (strip, row) space is flattened strip-major and cut into gridDim.x equal-cost ranges (a row of
+// a strip on the left / right image edge costs 3 units, an interior one 2: clamped window loads), so every CTA
+// gets the same amount of work whatever the image size; a range that crosses a strip boundary is run as two
+// (or more) passes of the pipeline.
+template <class G>
+__global__ void __launch_bounds__(G::THREADS, G::MINB) k_stream(const CascadeArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int strips = (a.w + G::WS - 1) / G::WS;
+    auto is_border = [&](int s) { return s * G::WS - G::HO(0) < 0 || s * G::WS + G::WS + G::HO(0) > a.w; };
+    long long total = 0;
+    for (int s = 0; s < strips; ++s) total += (long long)a.h * (is_border(s) ? 3 : 2);
+    const long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
+    long long beg = 0;
+    bool first = true;
+    for (int s = 0; s < strips; ++s) {
+        const bool border = is_border(s);
+        const int c = border ? 3 : 2;
+        const long long end = beg + (long long)a.h * c;
+        const long long ra = lo > beg ? lo : beg, rb = hi < end ? hi : end;
+        const long long cur = beg;
+        beg = end;
+        if (ra >= rb) continue;
+        StreamSched sc;
+        sc.y0 = (int)((ra - cur + c - 1) / c);
+        sc.y1 = (int)((rb - cur + c - 1) / c);
+        if (sc.y0 >= sc.y1) continue;
+        if (!first) __syncthreads();   // the rings are reused: the previous pass must be done reading them
+        first = false;
+        sc.f[G::NL] = sc.y0;
+        sc.e[G::NL] = sc.y1 - 1;
+#pragma unroll
+        for (int l = G::NL; l >= 1; --l) {
+            sc.i0[l] = sc.f[l] - G::R(l);
+            sc.f[l - 1] = max(sc.i0[l], 0);
+            sc.e[l - 1] = min(sc.e[l] + G::R(l), a.h - 1);
+        }
+        sc.r0 = sc.f[0];
+        sc.rlast = sc.e[0];
+        sc.T[1] = 0;
+#pragma unroll
+        for (int l = 1; l <= G::NL; ++l) {
+            sc.Tend[l] = sc.T[l] + (sc.e[l] + G::R(l) - sc.i0[l]);
+            if (l < G::NL) sc.T[l + 1] = sc.T[l] + 1 + G::R(l) + sc.f[l] - sc.i0[l];
+        }
+        sc.steps = sc.Tend[G::NL] + 1;
+        if (border)
+            stream_body<G, true>(a, smem, sc, s * G::WS);
+        else
+            stream_body<G, false>(a, smem, sc, s * G::WS);
+    }
+}
+
+// default scale space (radii 4,5,6 | 8,10)
+// (one warp per level: 24 / 28 / 32 and 26 / 32 threads of 4 columns)
+using StreamA = StreamGeom<3, 4, 5, 6, 4, 96, 12, 6, true>;    // G0 -> G1,G2,G3, D0,D1,D2, next base: 3 warps
+using StreamB = StreamGeom<2, 8, 10, 0, 4, 104, 12, 6, true>;  // G3 -> (G4,G5) -> D3,D4: 2 warps
+
+template <class G>
+cudaError_t launch_stream_t(const CascadeArgs& a, int sm_count, cudaStream_t s, int force_ctas = 0) {
+    const int strips = (a.w + G::WS - 1) / G::WS;
+    // one wave of CTAs, fewer when the image is too small to give each of them min_rows rows
+    const int min_rows = 48;
+    const long long units = ((long long)strips * a.h + min_rows - 1) / min_rows;
+    int ctas = sm_count * G::MINB;
+    if (units < ctas) ctas = (int)units;
+    if (force_ctas > 0) ctas = force_ctas;
+    k_stream<G><<<ctas, G::THREADS, G::kSmem, s>>>(a);
+    return cudaGetLastError();
+}
