@@ -141,8 +141,10 @@ int sift_b200_match_path(int na, int nb);
 #define SIFT_B200_PLANE_GAUSSIAN 0 /* layer 0..5 */
 #define SIFT_B200_PLANE_DOG 1      /* layer 0..4 */
 /* keep_all_planes: also store Gaussian layers 4 and 5 (the fused octave kernel keeps them on chip
- * otherwise; layers 0..3 and all DoG layers are always stored).  unfused_pyramid: build the scale
- * space with one kernel per level instead of the fused per-octave cascade (same results). */
+ * otherwise; layers 0..3 and all DoG layers are always stored).  unfused_pyramid selects the scale-space
+ * kernels (all give bit-identical planes): 0 = default (fused per-octave cascade: streaming kernels on large
+ * octaves, tile kernels on small ones), 1 = one kernel per level, 2 = fused tile kernels on every octave,
+ * 3 = fused streaming kernels on every octave. */
 int sift_b200_debug_options(sift_b200_ctx* ctx, int keep_all_planes, int unfused_pyramid);
 int sift_b200_debug_plane_dims(sift_b200_ctx* ctx, int octave, int* width, int* height);
 int sift_b200_debug_plane(sift_b200_ctx* ctx, int kind, int octave, int layer, float* host_out);

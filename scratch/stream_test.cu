@@ -54,7 +54,7 @@ static long long compare(const float* x, const float* y, int w, int h, int pitch
     return bad;
 }
 
-static int check(int w, int h, int segs) {
+static int check(int w, int h, int segs, bool onewarp) {
     const int pitch = (w + 31) & ~31;
     const size_t n = (size_t)pitch * h;
     Planes ref, neu; ref.alloc(n); neu.alloc(n);
@@ -69,7 +69,12 @@ static int check(int w, int h, int segs) {
         CascadeArgs ra = variant == 0 ? args_a(ref, w, h, pitch) : args_b(ref, w, h, pitch, true);
         CascadeArgs na = variant == 0 ? args_a(neu, w, h, pitch) : args_b(neu, w, h, pitch, true);
         cudaError_t e = variant == 0 ? launch_cascade_t<4, 5, 6>(ra, 148, 0) : launch_cascade_t<8, 10, 0>(ra, 148, 0);
-        if (e == cudaSuccess) e = variant == 0 ? launch_stream_t<StreamA>(na, 148, 0, segs) : launch_stream_t<StreamB>(na, 148, 0, segs);
+        using CA = StreamGeom<3, 4, 5, 6, 4, 96, 8, 8, true, true>;
+        using CB = StreamGeom<2, 8, 10, 0, 4, 104, 8, 8, true, true>;
+        if (e == cudaSuccess) {
+            if (onewarp) e = variant == 0 ? launch_stream_t<CA>(na, 148, 0, segs) : launch_stream_t<CB>(na, 148, 0, segs);
+            else e = variant == 0 ? launch_stream_t<StreamA>(na, 148, 0, segs) : launch_stream_t<StreamB>(na, 148, 0, segs);
+        }
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("  %dx%d variant %d: CUDA error %s\n", w, h, variant, cudaGetErrorString(e)); return 1; }
         const int nl = variant == 0 ? 3 : 2;
@@ -80,7 +85,7 @@ static int check(int w, int h, int segs) {
         }
         if (variant == 0 && ra.dec) bad += compare(ref.dec, neu.dec, ra.dec_w, ra.dec_h, ra.dec_pitch, "dec");
     }
-    printf("  %5d x %5d segs %d: %s\n", w, h, segs, bad ? "FAIL" : "bit-identical");
+    printf("  %5d x %5d ctas %d %s: %s\n", w, h, segs, onewarp ? "one-warp" : "warp-per-level", bad ? "FAIL" : "bit-identical");
     ref.release(); neu.release();
     return bad != 0;
 }
@@ -130,6 +135,15 @@ static void time_size(int w, int h) {
         printf("  tile cascade %c: %7.1f us\n", variant ? 'B' : 'A', best * 1e3);
     }
     time_variant<StreamA, StreamB>("stream A(4col,96) B(4col,104) 6/6", p, w, h, pitch, 0);
+    using A_1w = StreamGeom<3, 4, 5, 6, 4, 96, 8, 8, true, true>;
+    using B_1w = StreamGeom<2, 8, 10, 0, 4, 104, 8, 8, true, true>;
+    time_variant<A_1w, B_1w>("one-warp A 8/SM B 8/SM PF 8", p, w, h, pitch, 0);
+    using A_1w6 = StreamGeom<3, 4, 5, 6, 4, 96, 6, 9, true, true>;
+    using B_1w6 = StreamGeom<2, 8, 10, 0, 4, 104, 6, 8, true, true>;
+    time_variant<A_1w6, B_1w6>("one-warp A 9/SM B 8/SM PF 6", p, w, h, pitch, 0);
+    using A_1w12 = StreamGeom<3, 4, 5, 6, 4, 96, 6, 10, true, true>;
+    using B_1w12 = StreamGeom<2, 8, 10, 0, 4, 104, 6, 9, true, true>;
+    time_variant<A_1w12, B_1w12>("one-warp A 10/SM B 9/SM PF 6", p, w, h, pitch, 0);
 #ifdef QUICK
     p.release();
     return;
@@ -154,6 +168,12 @@ static void time_size(int w, int h) {
 
 int run(int argc, char** argv) {
     pyramid_init();
+    {
+        using CA = StreamGeom<3, 4, 5, 6, 4, 96, 8, 8, true, true>;
+        using CB = StreamGeom<2, 8, 10, 0, 4, 104, 8, 8, true, true>;
+        cudaFuncSetAttribute(k_stream<CA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CA::kSmem);
+        cudaFuncSetAttribute(k_stream<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB::kSmem);
+    }
     if (argc > 1 && !strcmp(argv[1], "prof")) {
         const int w = 7680, h = 4320, pitch = 7680;
         Planes p; p.alloc((size_t)pitch * h);
@@ -170,7 +190,7 @@ int run(int argc, char** argv) {
     const int sizes[][3] = {{40, 30, 0}, {230, 50, 0}, {300, 200, 0}, {300, 200, 3}, {1000, 700, 0}, {1000, 700, 5},
                             {225, 131, 2}, {7, 9, 0}, {1, 1, 0}, {2, 300, 4}, {960, 540, 0}, {1920, 1080, 0}, {449, 64, 1}};
 #ifndef QUICK
-    for (auto& s : sizes) fails += check(s[0], s[1], s[2]);
+    for (auto& s : sizes) { fails += check(s[0], s[1], s[2], false); fails += check(s[0], s[1], s[2], true); }
 #endif
     printf("%s\n", fails ? "SOME CHECKS FAILED" : "all checks bit-identical");
     if (argc > 1 && !strcmp(argv[1], "check")) return fails;

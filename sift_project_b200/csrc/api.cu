@@ -58,6 +58,7 @@ struct sift_b200_ctx {
     sift_b200_stats stats{};
     bool keep_planes = false;    // also store G[4], G[5] (debug plane access)
     bool force_unfused = false;  // per-level kernels instead of the fused octave cascade
+    int fused_mode = 0;          // launch_octave_fused mode: 0 auto, 2 tile kernels only, 3 streaming kernels only
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_stage;   // stage of the interval ending at event i (event 0: -1)
@@ -332,7 +333,7 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
                 OctaveDesc& nx = c->pyr.oct[o + 1];
                 dec = nx.G[0]; dw = nx.w; dh = nx.h; dp = nx.pitch;
             }
-            CU(c, launch_octave_fused(od, taps, dec, dw, dh, dp, c->keep_planes, c->sm_count, s));
+            CU(c, launch_octave_fused(od, taps, dec, dw, dh, dp, c->keep_planes, c->sm_count, c->fused_mode, s));
             prof_mark(c, SIFT_B200_STAGE_PYRAMID, 2);
         } else {
         for (int i = 1; i < layers; ++i) {
@@ -721,7 +722,8 @@ int sift_b200_match_path(int na, int nb) { return match_uses_tensor_cores(na, nb
 int sift_b200_debug_options(sift_b200_ctx* c, int keep_all_planes, int unfused_pyramid) {
     if (!c) return SIFT_B200_E_INVALID;
     c->keep_planes = keep_all_planes != 0;
-    c->force_unfused = unfused_pyramid != 0;
+    c->force_unfused = unfused_pyramid == 1;
+    c->fused_mode = unfused_pyramid == 2 || unfused_pyramid == 3 ? unfused_pyramid : 0;
     return SIFT_B200_OK;
 }
 

@@ -615,8 +615,13 @@ bool cascade_supported(const BlurTaps* taps) {
 }
 
 // One octave: G[0] -> G[1..3], D[0..4], next base.  keep_all also stores G[4], G[5] (debug planes).
+// mode: 0 = streaming kernels (stream.cuh) on octaves large enough to profit, tile kernels below; 2 = tile kernels
+// only; 3 = streaming kernels on every octave (tests).  All three give bit-identical planes.
 cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, float* dec, int dec_w, int dec_h,
-                                int dec_pitch, bool keep_all, int sm_count, cudaStream_t s) {
+                                int dec_pitch, bool keep_all, int sm_count, int mode, cudaStream_t s) {
+    // measured on B200 (scratch/stream_test.cu): 7680 x 4320 tile 303 + 249 us, streaming 261 + 214 us;
+    // 3840 x 2160 equal; smaller octaves are faster as tiles
+    const bool stream = mode == 3 || (mode == 0 && (long long)od.w * od.h >= (20ll << 20));
     CascadeArgs a;
     a.in = od.G[0];
     a.g[0] = od.G[1]; a.g[1] = od.G[2]; a.g[2] = od.G[3];
@@ -624,7 +629,7 @@ cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, floa
     a.dec = dec; a.dec_w = dec_w; a.dec_h = dec_h; a.dec_pitch = dec_pitch;
     a.w = od.w; a.h = od.h; a.pitch = od.pitch;
     a.taps[0] = taps[1]; a.taps[1] = taps[2]; a.taps[2] = taps[3];
-    cudaError_t e = launch_cascade_t<4, 5, 6>(a, sm_count, s);
+    cudaError_t e = stream ? launch_stream_t<StreamA>(a, sm_count, s) : launch_cascade_t<4, 5, 6>(a, sm_count, s);
     if (e != cudaSuccess) return e;
     CascadeArgs b;
     b.in = od.G[3];
@@ -633,7 +638,7 @@ cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, floa
     b.dec = nullptr; b.dec_w = b.dec_h = b.dec_pitch = 0;
     b.w = od.w; b.h = od.h; b.pitch = od.pitch;
     b.taps[0] = taps[4]; b.taps[1] = taps[5]; b.taps[2] = taps[5];
-    return launch_cascade_t<8, 10, 0>(b, sm_count, s);
+    return stream ? launch_stream_t<StreamB>(b, sm_count, s) : launch_cascade_t<8, 10, 0>(b, sm_count, s);
 }
 
 cudaError_t launch_prepare_u8(const uint8_t* src, int sw, int sh, int ch, float* dst, int dw, int dh,

@@ -353,9 +353,10 @@ __global__ void __launch_bounds__(G::THREADS, G::MINB) k_stream(const CascadeArg
 }
 
 // default scale space (radii 4,5,6 | 8,10)
-// (one warp per level: 24 / 28 / 32 and 26 / 32 threads of 4 columns)
-using StreamA = StreamGeom<3, 4, 5, 6, 4, 96, 12, 6, true>;    // G0 -> G1,G2,G3, D0,D1,D2, next base: 3 warps
-using StreamB = StreamGeom<2, 8, 10, 0, 4, 104, 12, 6, true>;  // G3 -> (G4,G5) -> D3,D4: 2 warps
+// A: one warp per level (32 / 28 / 24 threads of 4 columns), 5 CTAs per SM (6 would cap the registers at 96 and
+// spill); B: two warps per level (64 / 58 threads), 3 CTAs per SM.  Measured alternatives in DESIGN.md.
+using StreamA = StreamGeom<3, 4, 5, 6, 4, 96, 12, 5, true>;    // G0 -> G1,G2,G3, D0,D1,D2, next base
+using StreamB = StreamGeom<2, 8, 10, 0, 4, 232, 12, 3, true>;  // G3 -> (G4,G5) -> D3,D4
 
 template <class G>
 cudaError_t launch_stream_t(const CascadeArgs& a, int sm_count, cudaStream_t s, int force_ctas = 0) {

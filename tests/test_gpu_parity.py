@@ -346,23 +346,42 @@ def test_match_large_tc_vs_simt(ctx, force_path):
 
 
 def test_fused_octave_cascade_equals_per_level_kernels(ctx):
-    """The fused per-octave cascade (k_cascade) and the one-kernel-per-level path run the same
-    arithmetic in the same order: every plane and the final records are bit-identical, including
-    image sizes that are not multiples of the tile and octaves smaller than one tile."""
+    """The fused per-octave cascades -- tile kernels (k_cascade, mode 2), streaming kernels (k_stream,
+    mode 3) and the default mix of the two (mode 0) -- and the one-kernel-per-level path (mode 1) run
+    the same arithmetic in the same order: every plane and the final records are bit-identical,
+    including image sizes that are not multiples of the tile / strip and octaves smaller than one."""
     for h, w, seed in ((192, 256, 42), (301, 517, 7), (97, 1030, 8), (768, 1024, 9)):
         img = O.synth_image(h, w, seed=seed)
-        ctx.debug_options(keep_all_planes=True, unfused_pyramid=True)
+        ctx.debug_options(keep_all_planes=True, unfused_pyramid=1)
         ref = ctx.detect(img)
         octs = ctx.stats()["octaves"]
         planes = [[ctx.gaussian(o, l) for l in range(6)] + [ctx.dog(o, l) for l in range(5)] for o in range(octs)]
-        ctx.debug_options(keep_all_planes=True, unfused_pyramid=False)
-        got = ctx.detect(img)
-        for o in range(octs):
-            mine = [ctx.gaussian(o, l) for l in range(6)] + [ctx.dog(o, l) for l in range(5)]
-            for k, (x, y) in enumerate(zip(mine, planes[o])):
-                assert np.array_equal(x, y), (h, w, o, k, float(np.abs(x - y).max()))
-        assert got.tobytes() == ref.tobytes(), (h, w)
+        for mode in (0, 2, 3):
+            ctx.debug_options(keep_all_planes=True, unfused_pyramid=mode)
+            got = ctx.detect(img)
+            for o in range(octs):
+                mine = [ctx.gaussian(o, l) for l in range(6)] + [ctx.dog(o, l) for l in range(5)]
+                for k, (x, y) in enumerate(zip(mine, planes[o])):
+                    assert np.array_equal(x, y), (mode, h, w, o, k, float(np.abs(x - y).max()))
+            assert got.tobytes() == ref.tobytes(), (mode, h, w)
     ctx.debug_options()
+
+
+def test_streaming_cascade_on_a_large_octave():
+    """Default mode at a size where octave 0 takes the streaming kernels (>= 20 Mpx) and the rest the tile
+    kernels: same bytes as tile kernels everywhere and as streaming kernels everywhere, without the debug
+    planes (G4, G5 stay on chip).  Width 3000 -> base 6000 x 3600: strips of 96 / 232 columns do not divide it."""
+    img = O.synth_image(1800, 3000, seed=11)
+    with S.SiftContext(3000, 1800) as c:
+        c.debug_options(unfused_pyramid=2)
+        ref = c.detect(img)
+        c.debug_options(unfused_pyramid=0)
+        got = c.detect(img)
+        c.debug_options(unfused_pyramid=3)
+        got3 = c.detect(img)
+    assert len(ref) > 5000
+    assert got.tobytes() == ref.tobytes()
+    assert got3.tobytes() == ref.tobytes()
 
 
 # ------------------------------------------------------------------------------------------
@@ -510,11 +529,12 @@ def test_random_shapes_fused_equals_per_level(ctx):
     for h, w in shapes:
         img = O.synth_image(h, w, seed=h * 1000 + w)
         for doubled in (True, False):
-            ctx.debug_options(unfused_pyramid=True)
+            ctx.debug_options(unfused_pyramid=1)
             ref = ctx.detect(img, double_image_size=doubled)
-            ctx.debug_options(unfused_pyramid=False)
-            got = ctx.detect(img, double_image_size=doubled)
-            assert got.tobytes() == ref.tobytes(), (h, w, doubled)
+            for mode in (2, 3):   # tile cascade, streaming cascade
+                ctx.debug_options(unfused_pyramid=mode)
+                got = ctx.detect(img, double_image_size=doubled)
+                assert got.tobytes() == ref.tobytes(), (mode, h, w, doubled)
     ctx.debug_options()
 
 
