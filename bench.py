@@ -369,7 +369,7 @@ def run_b200(args):
         except Exception:
             pass
         total_ms = sum(stages.values())
-        roof = {"bound": "hbm", "kernel": "pyramid: k_cascade<4,5,6> + k_cascade<8,10,0>, all octaves of one image", "achieved": achieved,
+        roof = {"bound": "hbm", "kernel": "pyramid: fused cascade G0->G1..G3,D0..D2,next base + G3->D3,D4 (k_stream on octaves >= 20 Mpx, k_cascade below), all octaves of one image", "achieved": achieved,
                 "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                 "algorithmic_bytes": pyr_bytes, "ms": stages["pyramid"], "launches": nl["pyramid"],
                 "peak_source": peak_src,

@@ -466,6 +466,11 @@ int sift_b200_create(int device, int max_width, int max_height, sift_b200_ctx** 
     if (!c) return fail(nullptr, SIFT_B200_E_INVALID, "out of host memory");
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (const char* m = getenv("SIFT_B200_PYRAMID_MODE")) {   // experiments: same values as sift_b200_debug_options
+        const int v = atoi(m);
+        c->force_unfused = v == 1;
+        c->fused_mode = v == 2 || v == 3 ? v : 0;
+    }
     c->max_w = max_width;
     c->max_h = max_height;
 #define CRT(call)                                                                                   \

@@ -7,6 +7,7 @@
 // convert_to_grayscale + resize_inter_bilinear (image.cpp:8-24, 62-88) as the input stage.
 //
 // HBM-bound by design: one read of G[i-1], one write of G[i], one write of D[i-1] per level.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -619,9 +620,16 @@ bool cascade_supported(const BlurTaps* taps) {
 // only; 3 = streaming kernels on every octave (tests).  All three give bit-identical planes.
 cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, float* dec, int dec_w, int dec_h,
                                 int dec_pitch, bool keep_all, int sm_count, int mode, cudaStream_t s) {
-    // measured on B200 (scratch/stream_test.cu): 7680 x 4320 tile 303 + 249 us, streaming 261 + 214 us;
-    // 3840 x 2160 equal; smaller octaves are faster as tiles
-    const bool stream = mode == 3 || (mode == 0 && (long long)od.w * od.h >= (20ll << 20));
+    // Measured on B200.  Alone on the GPU (scratch/stream_test.cu): 7680 x 4320 tile 303 + 249 us, streaming
+    // 261 + 214 us; 3840 x 2160 equal (170 us); below that the tile kernels are faster (the pipeline fill of
+    // ~35 rows per CTA is pure latency).  With four images in flight the streaming kernels (small CTAs, 24-55 KB
+    // of shared memory) share the SMs better with the other images' kernels: 4K batch images/s by threshold
+    // 20 Mpx 548, 8 Mpx 552, 2 Mpx 563, 0.5 Mpx 562, all octaves 555 against 511 with tile kernels only, while
+    // the single-image pyramid time goes 0.869 / 0.874 / 0.910 / 0.963 / 1.27 ms.  8 Mpx keeps both.
+    // SIFT_B200_STREAM_MIN_PX overrides the threshold (experiments).
+    static const long long min_px =
+        getenv("SIFT_B200_STREAM_MIN_PX") ? atoll(getenv("SIFT_B200_STREAM_MIN_PX")) : 8000000ll;
+    const bool stream = mode == 3 || (mode == 0 && (long long)od.w * od.h >= min_px);
     CascadeArgs a;
     a.in = od.G[0];
     a.g[0] = od.G[1]; a.g[1] = od.G[2]; a.g[2] = od.G[3];
