@@ -349,12 +349,15 @@ def run_b200(args):
         c0 = ctxs[0]
         c0.set_profiling(True)
         acc = None
+        marks_acc = None
         reps = min(len(d_imgs), 16)
         for k in range(reps + 2):
             c0.detect_enqueue(d_imgs[k % len(d_imgs)], W, H)
             ms, nl = c0.profile()
+            marks = c0.profile_marks()
             if k >= 2:
                 acc = ms if acc is None else {s: acc[s] + ms[s] for s in ms}
+                marks_acc = [t for _, t in marks] if marks_acc is None else [a + t for a, (_, t) in zip(marks_acc, marks)]
         c0.set_profiling(False)
         stages = {s: acc[s] / reps for s in acc}
         stage_launches = nl
@@ -369,10 +372,24 @@ def run_b200(args):
         except Exception:
             pass
         total_ms = sum(stages.values())
+        # per-kernel view of octave 0 (the two largest launches): live event times of the two fused kernels;
+        # algorithmic bytes per octave pixel: first kernel reads G0 (4), writes G1..G3, D0..D2 (24) and the next
+        # base (1); second kernel reads G3 (4), writes D3, D4 (8)
+        per_kernel = None
+        pyr_marks = [i for i, (st, _) in enumerate(marks) if st == "pyramid"]
+        if len(pyr_marks) >= 2 and nl["pyramid"] == 2 * (len(pyr_marks) - 1):   # fused path: octave 0 kernel by kernel
+            bw, bh = (2 * W, 2 * H)
+            px0 = bw * bh
+            per_kernel = []
+            for name, idx, bpp in (("octave 0: G0 -> G1..G3, D0..D2, next base", pyr_marks[0], 29.0),
+                                   ("octave 0: G3 -> (G4, G5 on chip) -> D3, D4", pyr_marks[1], 12.0)):
+                t = marks_acc[idx] / reps
+                per_kernel.append({"kernel": name, "ms": t, "algorithmic_bytes": bpp * px0,
+                                   "achieved": bpp * px0 / (t * 1e-3) / 1e9, "frac": bpp * px0 / (t * 1e-3) / 1e9 / hbm_peak})
         roof = {"bound": "hbm", "kernel": "pyramid: fused cascade G0->G1..G3,D0..D2,next base + G3->D3,D4 (k_stream on octaves >= 20 Mpx, k_cascade below), all octaves of one image", "achieved": achieved,
                 "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                 "algorithmic_bytes": pyr_bytes, "ms": stages["pyramid"], "launches": nl["pyramid"],
-                "peak_source": peak_src,
+                "peak_source": peak_src, "per_kernel": per_kernel,
                 "whole_detect": {"algorithmic_bytes": HBM_BYTES_PER_INPUT_PIXEL * W * H, "ms": total_ms,
                                  "frac": HBM_BYTES_PER_INPUT_PIXEL * W * H / (total_ms * 1e-3) / 1e9 / hbm_peak}}
 

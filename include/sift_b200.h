@@ -170,6 +170,10 @@ int sift_b200_set_profiling(sift_b200_ctx* ctx, int on);
 /* Milliseconds and kernel-launch counts per stage of the last profiled detect (arrays of
  * SIFT_B200_STAGE_COUNT); waits for the stream. */
 int sift_b200_get_profile(sift_b200_ctx* ctx, float* stage_ms, int32_t* stage_launches);
+/* The same profile unaggregated: one (stage, milliseconds) entry per bracketed group of launches, in issue
+ * order (input; octave 0 first pyramid kernel, octave 0 second pyramid kernel, octave 0 extrema; octave 1
+ * pyramid (both kernels), octave 1 extrema; ...; refine; ...).  *count = entries available; at most `capacity` are written. */
+int sift_b200_get_profile_marks(sift_b200_ctx* ctx, int32_t* stage, float* ms, int capacity, int* count);
 
 #ifdef __cplusplus
 }

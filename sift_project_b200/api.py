@@ -100,6 +100,7 @@ def load_library():
         "sift_b200_result_copy": (i32, [vp, vp, i32, i32p]),
         "sift_b200_set_profiling": (i32, [vp, i32]),
         "sift_b200_get_profile": (i32, [vp, vp, vp]),
+        "sift_b200_get_profile_marks": (i32, [vp, vp, vp, i32, i32p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -210,6 +211,15 @@ class SiftContext:
         nl = np.zeros(len(self.STAGES), np.int32)
         self._check(self._L.sift_b200_get_profile(self._h, ms.ctypes.data, nl.ctypes.data))
         return dict(zip(self.STAGES, ms.tolist())), dict(zip(self.STAGES, nl.tolist()))
+
+    def profile_marks(self):
+        """[(stage name, ms)] per bracketed group of launches of the last profiled detect, in issue order."""
+        n = C.c_int(0)
+        self._check(self._L.sift_b200_get_profile_marks(self._h, None, None, 0, C.byref(n)))
+        st = np.zeros(n.value, np.int32)
+        ms = np.zeros(n.value, np.float32)
+        self._check(self._L.sift_b200_get_profile_marks(self._h, st.ctypes.data, ms.ctypes.data, n.value, C.byref(n)))
+        return [(self.STAGES[s] if 0 <= s < len(self.STAGES) else "other", float(t)) for s, t in zip(st, ms)]
 
     def detect_finish(self):
         n = C.c_int(0)

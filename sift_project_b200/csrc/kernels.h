@@ -18,7 +18,7 @@ cudaError_t launch_input_u8(const uint8_t* src, int sw, int sh, float* dst, int 
                             const BlurTaps& taps, cudaStream_t s);
 bool cascade_supported(const BlurTaps* taps);
 cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, float* dec, int dec_w, int dec_h,
-                                int dec_pitch, bool keep_all, int sm_count, int mode, cudaStream_t s);
+                                int dec_pitch, bool keep_all, int sm_count, int mode, int part, cudaStream_t s);
 
 // detect.cu
 struct SortScratch {

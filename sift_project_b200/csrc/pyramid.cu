@@ -618,8 +618,9 @@ bool cascade_supported(const BlurTaps* taps) {
 // One octave: G[0] -> G[1..3], D[0..4], next base.  keep_all also stores G[4], G[5] (debug planes).
 // mode: 0 = streaming kernels (stream.cuh) on octaves large enough to profit, tile kernels below; 2 = tile kernels
 // only; 3 = streaming kernels on every octave (tests).  All three give bit-identical planes.
+// part: 1 = the G0 -> G1..G3 kernel, 2 = the G3 -> D3, D4 kernel (the caller brackets each with profiling events).
 cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, float* dec, int dec_w, int dec_h,
-                                int dec_pitch, bool keep_all, int sm_count, int mode, cudaStream_t s) {
+                                int dec_pitch, bool keep_all, int sm_count, int mode, int part, cudaStream_t s) {
     // Measured on B200.  Alone on the GPU (scratch/stream_test.cu): 7680 x 4320 tile 303 + 249 us, streaming
     // 261 + 214 us; 3840 x 2160 equal (170 us); below that the tile kernels are faster (the pipeline fill of
     // ~35 rows per CTA is pure latency).  With four images in flight the streaming kernels (small CTAs, 24-55 KB
@@ -637,8 +638,7 @@ cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, floa
     a.dec = dec; a.dec_w = dec_w; a.dec_h = dec_h; a.dec_pitch = dec_pitch;
     a.w = od.w; a.h = od.h; a.pitch = od.pitch;
     a.taps[0] = taps[1]; a.taps[1] = taps[2]; a.taps[2] = taps[3];
-    cudaError_t e = stream ? launch_stream_t<StreamA>(a, sm_count, s) : launch_cascade_t<4, 5, 6>(a, sm_count, s);
-    if (e != cudaSuccess) return e;
+    if (part == 1) return stream ? launch_stream_t<StreamA>(a, sm_count, s) : launch_cascade_t<4, 5, 6>(a, sm_count, s);
     CascadeArgs b;
     b.in = od.G[3];
     b.g[0] = keep_all ? od.G[4] : nullptr; b.g[1] = keep_all ? od.G[5] : nullptr; b.g[2] = nullptr;
