@@ -69,8 +69,8 @@ static int check(int w, int h, int segs, bool onewarp) {
         CascadeArgs ra = variant == 0 ? args_a(ref, w, h, pitch) : args_b(ref, w, h, pitch, true);
         CascadeArgs na = variant == 0 ? args_a(neu, w, h, pitch) : args_b(neu, w, h, pitch, true);
         cudaError_t e = variant == 0 ? launch_cascade_t<4, 5, 6>(ra, 148, 0) : launch_cascade_t<8, 10, 0>(ra, 148, 0);
-        using CA = StreamGeom<3, 4, 5, 6, 4, 96, 8, 8, true, true>;
-        using CB = StreamGeom<2, 8, 10, 0, 4, 104, 8, 8, true, true>;
+        using CA = StreamGeom<3, 4, 5, 6, 2, 96, 12, 4, true, 1>;
+        using CB = StreamGeom<2, 8, 10, 0, 2, 104, 6, 5, true, 2>;
         if (e == cudaSuccess) {
             if (onewarp) e = variant == 0 ? launch_stream_t<CA>(na, 148, 0, segs) : launch_stream_t<CB>(na, 148, 0, segs);
             else e = variant == 0 ? launch_stream_t<StreamA>(na, 148, 0, segs) : launch_stream_t<StreamB>(na, 148, 0, segs);
@@ -85,15 +85,17 @@ static int check(int w, int h, int segs, bool onewarp) {
         }
         if (variant == 0 && ra.dec) bad += compare(ref.dec, neu.dec, ra.dec_w, ra.dec_h, ra.dec_pitch, "dec");
     }
-    printf("  %5d x %5d ctas %d %s: %s\n", w, h, segs, onewarp ? "one-warp" : "warp-per-level", bad ? "FAIL" : "bit-identical");
+    printf("  %5d x %5d ctas %d %s: %s\n", w, h, segs, onewarp ? "2 columns/thread" : "default", bad ? "FAIL" : "bit-identical");
     ref.release(); neu.release();
     return bad != 0;
 }
 
 template <class GA, class GB>
 static void time_variant(const char* name, Planes& p, int w, int h, int pitch, int segs) {
-    cudaFuncSetAttribute(k_stream<GA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GA::kSmem);
-    cudaFuncSetAttribute(k_stream<GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB::kSmem);
+    cudaFuncSetAttribute(k_stream<GA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GA::kSmem);
+    cudaFuncSetAttribute(k_stream<GB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB::kSmem);
+    cudaFuncSetAttribute(k_stream<GA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GA::kSmem);
+    cudaFuncSetAttribute(k_stream<GB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB::kSmem);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best[2] = {1e9f, 1e9f};
     for (int variant = 0; variant < 2; ++variant) {
@@ -108,8 +110,8 @@ static void time_variant(const char* name, Planes& p, int w, int h, int pitch, i
         }
     }
     int occA = 0, occB = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, k_stream<GA>, GA::THREADS, GA::kSmem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, k_stream<GB>, GB::THREADS, GB::kSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, k_stream<GA, true>, GA::THREADS, GA::kSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, k_stream<GB, false>, GB::THREADS, GB::kSmem);
     printf("  %-34s segs %2d: A %7.1f us  B %7.1f us  sum %7.1f us  (CTAs/SM %d / %d, smem %zu / %zu)\n", name, segs,
            best[0] * 1e3, best[1] * 1e3, (best[0] + best[1]) * 1e3, occA, occB, GA::kSmem, GB::kSmem);
 }
@@ -135,15 +137,12 @@ static void time_size(int w, int h) {
         printf("  tile cascade %c: %7.1f us\n", variant ? 'B' : 'A', best * 1e3);
     }
     time_variant<StreamA, StreamB>("stream A(4col,96) B(4col,104) 6/6", p, w, h, pitch, 0);
-    using A_1w = StreamGeom<3, 4, 5, 6, 4, 96, 8, 8, true, true>;
-    using B_1w = StreamGeom<2, 8, 10, 0, 4, 104, 8, 8, true, true>;
-    time_variant<A_1w, B_1w>("one-warp A 8/SM B 8/SM PF 8", p, w, h, pitch, 0);
-    using A_1w6 = StreamGeom<3, 4, 5, 6, 4, 96, 6, 9, true, true>;
-    using B_1w6 = StreamGeom<2, 8, 10, 0, 4, 104, 6, 8, true, true>;
-    time_variant<A_1w6, B_1w6>("one-warp A 9/SM B 8/SM PF 6", p, w, h, pitch, 0);
-    using A_1w12 = StreamGeom<3, 4, 5, 6, 4, 96, 6, 10, true, true>;
-    using B_1w12 = StreamGeom<2, 8, 10, 0, 4, 104, 6, 9, true, true>;
-    time_variant<A_1w12, B_1w12>("one-warp A 10/SM B 9/SM PF 6", p, w, h, pitch, 0);
+    using A_k2 = StreamGeom<3, 4, 5, 6, 4, 96, 6, 4, true, 2>;
+    using B_k1 = StreamGeom<2, 8, 10, 0, 4, 232, 12, 3, true, 1>;
+    time_variant<A_k2, B_k1>("A K=2 4/SM PF6, B(232) K=1 PF12", p, w, h, pitch, 0);
+    using A_c2b = StreamGeom<3, 4, 5, 6, 2, 96, 12, 4, true, 1>;
+    using B_c2d = StreamGeom<2, 8, 10, 0, 2, 104, 6, 5, true, 2>;
+    time_variant<A_c2b, B_c2d>("C=2: A 4/SM, B(104) 5/SM K=2", p, w, h, pitch, 0);
 #ifdef QUICK
     p.release();
     return;
@@ -169,10 +168,10 @@ static void time_size(int w, int h) {
 int run(int argc, char** argv) {
     pyramid_init();
     {
-        using CA = StreamGeom<3, 4, 5, 6, 4, 96, 8, 8, true, true>;
-        using CB = StreamGeom<2, 8, 10, 0, 4, 104, 8, 8, true, true>;
-        cudaFuncSetAttribute(k_stream<CA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CA::kSmem);
-        cudaFuncSetAttribute(k_stream<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB::kSmem);
+        using CA = StreamGeom<3, 4, 5, 6, 2, 96, 12, 4, true, 1>;
+        using CB = StreamGeom<2, 8, 10, 0, 2, 104, 6, 5, true, 2>;
+        cudaFuncSetAttribute(k_stream<CA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CA::kSmem);
+        cudaFuncSetAttribute(k_stream<CB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB::kSmem);
     }
     if (argc > 1 && !strcmp(argv[1], "prof")) {
         const int w = 7680, h = 4320, pitch = 7680;

@@ -573,10 +573,13 @@ cudaError_t pyramid_init() {
     SB_CASC_ATTR(4, 5, 6, CTW, TH, CCT, 2) SB_CASC_ATTR(8, 10, 0, CTW, TH, CCT, 2)
     SB_CASC_ATTR(4, 5, 6, 32, 32, 128, 4) SB_CASC_ATTR(8, 10, 0, 32, 32, 128, 4)
 #undef SB_CASC_ATTR
-    if ((e = cudaFuncSetAttribute(k_stream<StreamA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)StreamA::kSmem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_stream<StreamB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)StreamB::kSmem)) != cudaSuccess) return e;
+#define SB_STREAM_ATTR(G, SG)                                                                              \
+    if ((e = cudaFuncSetAttribute(k_stream<G, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmem)) != \
+        cudaSuccess)                                                                                      \
+        return e;
+    SB_STREAM_ATTR(StreamA, true) SB_STREAM_ATTR(StreamA, false) SB_STREAM_ATTR(StreamB, true)
+    SB_STREAM_ATTR(StreamB, false)
+#undef SB_STREAM_ATTR
 #define SB_INIT(R) if ((e = init_blur_r<R>()) != cudaSuccess) return e;
     SB_INIT(1) SB_INIT(2) SB_INIT(3) SB_INIT(4) SB_INIT(5) SB_INIT(6) SB_INIT(7) SB_INIT(8)
     SB_INIT(9) SB_INIT(10) SB_INIT(11) SB_INIT(12) SB_INIT(13) SB_INIT(14) SB_INIT(15) SB_INIT(16)

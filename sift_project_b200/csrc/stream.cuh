@@ -34,9 +34,10 @@ struct StreamSched {
     int steps;
 };
 
-template <int NL_, int R1_, int R2_, int R3_, int C_, int WS_, int PF_, int MINB_, bool PACK_>
+template <int NL_, int R1_, int R2_, int R3_, int C_, int WS_, int PF_, int MINB_, bool PACK_, int K_ = 1>
 struct StreamGeom {
     static constexpr int NL = NL_, C = C_, WS = WS_, PF = PF_, MINB = MINB_;
+    static constexpr int K = K_;   // rows per step (and per CTA barrier)
     static constexpr bool PACK = PACK_;
     __host__ __device__ static constexpr int R(int l) { return l == 1 ? R1_ : l == 2 ? R2_ : l == 3 ? R3_ : 0; }
     __host__ __device__ static constexpr int RA(int l) { return ru4(R(l)); }
@@ -48,10 +49,12 @@ struct StreamGeom {
     __host__ __device__ static constexpr int FIRSTWARP(int l) { return l <= 1 ? 0 : FIRSTWARP(l - 1) + WARPS(l - 1); }
     static constexpr int THREADS = 32 * (FIRSTWARP(NL) + WARPS(NL));
     // ring depths: see the schedule in k_stream
-    __host__ __device__ static constexpr int DEPTH(int l) { return l == 0 ? PF + 2 * R(1) + 2 : 2 * R(l + 1) + 2; }
+    __host__ __device__ static constexpr int DEPTH(int l) {
+        return l == 0 ? K * PF + 2 * R(1) + 3 * K - 1 : 2 * R(l + 1) + 3 * K - 1;
+    }
     __host__ __device__ static constexpr int OFF(int l) { return l <= 0 ? 0 : OFF(l - 1) + DEPTH(l - 1) * W(l - 1); }
     static constexpr size_t kSmem = (size_t)OFF(NL) * sizeof(float);
-    static_assert(WS % C == 0 && C % 4 == 0, "strip width / columns per thread");
+    static_assert(WS % C == 0 && C % 2 == 0, "strip width / columns per thread");
 };
 
 __device__ __forceinline__ void stream_bar() {
@@ -93,6 +96,8 @@ struct StreamFetch {
         }
     }
     __device__ __forceinline__ void next() {
+#pragma unroll
+        for (int kk = 0; kk < G::K; ++kk)
         if (rows_left > 0) {
 #pragma unroll
             for (int k = 0; k < PER; ++k)
@@ -111,7 +116,7 @@ struct StreamFetch {
 // One level of the pipeline, run by the warps of that level.  rt = thread index inside the level.
 // Everything that moves with the row (ring slots, plane offsets) is a running counter: no division, no
 // 64-bit multiply inside the step.
-template <class G, int L, bool BORDER>
+template <class G, int L, bool BORDER, bool STORE_G>
 __device__ __forceinline__ void stream_level(const CascadeArgs& a, float* smem, const int rt,
                                              const StreamSched& sc, const int sx0) {
     constexpr int R = G::R(L), RA = G::RA(L), C = G::C, C2 = C / 2;
@@ -141,16 +146,13 @@ __device__ __forceinline__ void stream_level(const CascadeArgs& a, float* smem, 
     for (int p = 0; p < 2 * R; ++p)
 #pragma unroll
         for (int c = 0; c < C2; ++c) acc[p][c] = make_float2(0.f, 0.f);
-    float2 w2[R + 1];
-#pragma unroll
-    for (int d = 0; d <= R; ++d) w2[d] = make_float2(tp.w[d], tp.w[d]);
-
     const int T = sc.T[L], Tend = sc.Tend[L], steps = sc.steps;
     const int fL = sc.f[L], eL = sc.e[L];
     const int i0 = sc.i0[L];
     auto mod = [](int v, int m) { return ((v % m) + m) % m; };
     // running state of the step loop
-    int i = i0;                                            // virtual input row
+    constexpr int K = G::K;
+    int i = i0;                                            // virtual input row of the first of the K rows of a step
     int in_off = (min(max(i0, 0), h - 1) % DP) * WP;       // ring slot (floats) of the clamped input row
     int cen_off = mod(i0 - R, DP) * WP;                    // ... of the previous level's row y (DoG centre)
     int out_off = mod(i0 - R, DL) * WL;                    // ... of this level's row y
@@ -171,140 +173,175 @@ __device__ __forceinline__ void stream_level(const CascadeArgs& a, float* smem, 
         }
         stream_bar();
         if (t < T || t > Tend) continue;   // pipeline fill / drain: this level has nothing to do
-        const float* rowp = ringP + in_off;
-        // ---- horizontal pass of one row: C outputs from a register window ----
-        float v[C + 2 * RA];
-        if (!BORDER) {
-            const float4* src = reinterpret_cast<const float4*>(rowp + x);
+        // ---- horizontal pass of K rows: C outputs each from a register window ----
+        float2 hv[K][C2];
 #pragma unroll
-            for (int k = 0; k < (C + 2 * RA) / 4; ++k) {
-                if (4 * k + 3 < RA - R || 4 * k >= RA + C + R) continue;   // outside the taps
-                const float4 q = src[k];
-                v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+        for (int k = 0; k < K; ++k) {
+            const float* rowp = ringP + in_off;
+            float v[C + 2 * RA];
+            if (!BORDER) {
+                if (C % 4 == 0) {
+                    const float4* src = reinterpret_cast<const float4*>(rowp + x);
+#pragma unroll
+                    for (int q4 = 0; q4 < (C + 2 * RA) / 4; ++q4) {
+                        if (4 * q4 + 3 < RA - R || 4 * q4 >= RA + C + R) continue;   // outside the taps
+                        const float4 q = src[q4];
+                        v[4 * q4] = q.x; v[4 * q4 + 1] = q.y; v[4 * q4 + 2] = q.z; v[4 * q4 + 3] = q.w;
+                    }
+                } else {   // two columns per thread: x is only 8-byte aligned
+                    const float2* src = reinterpret_cast<const float2*>(rowp + x);
+#pragma unroll
+                    for (int q2 = 0; q2 < (C + 2 * RA) / 2; ++q2) {
+                        if (2 * q2 + 1 < RA - R || 2 * q2 >= RA + C + R) continue;
+                        const float2 q = src[q2];
+                        v[2 * q2] = q.x; v[2 * q2 + 1] = q.y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = RA - R; j < RA + C + R; ++j) v[j] = rowp[min(max(x + j, clo), chi)];
             }
-        } else {
 #pragma unroll
-            for (int k = RA - R; k < RA + C + R; ++k) v[k] = rowp[min(max(x + k, clo), chi)];
-        }
-        float2 hv[C2];
+            for (int c = 0; c < C; ++c) {
+                float sacc = 0.f;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            float sacc = 0.f;
-#pragma unroll
-            for (int u = R; u >= 1; --u) sacc = fmaf(tp.w[u], v[RA + c - u] + v[RA + c + u], sacc);
-            const float o = fmaf(tp.w[0], v[RA + c], sacc);
-            if (c & 1) hv[c / 2].y = o; else hv[c / 2].x = o;
+                for (int u = R; u >= 1; --u) sacc = fmaf(tp.w[u], v[RA + c - u] + v[RA + c + u], sacc);
+                const float o = fmaf(tp.w[0], v[RA + c], sacc);
+                if (c & 1) hv[k][c / 2].y = o; else hv[k][c / 2].x = o;
+            }
+            if ((unsigned)(i + k) < (unsigned)(h - 1)) {   // rows above / below the image re-read the edge row
+                in_off += WP;
+                if (in_off == DP * WP) in_off = 0;
+            }
         }
         // ---- vertical pass, scatter form: row i adds w[|i - y|] * h to every output row y in [i-R, i+R].  The
-        // accumulators move down one slot per step THROUGH the FMA (d = a * b + c with c = slot p+1, d = slot p):
+        // accumulators move down one slot per row THROUGH the FMA (d = a * b + c with c = slot p+1, d = slot p):
         // the rotation costs nothing, every index is static, and each row still receives its terms in ascending
         // input-row order starting from fma(w[R], h, 0) ----
-        float2 out[C2];
+        float2 out[K][C2];
 #pragma unroll
-        for (int c = 0; c < C2; ++c) {
-            if (G::PACK) {
-                out[c] = __ffma2_rn(w2[R], hv[c], acc[0][c]);
-            } else {
-                out[c].x = fmaf(tp.w[R], hv[c].x, acc[0][c].x);
-                out[c].y = fmaf(tp.w[R], hv[c].y, acc[0][c].y);
-            }
-        }
-#ifdef SB_EXP_NOV
-        if (hv[0].x == 123.456f)
-#endif
-#pragma unroll
-        for (int p = 0; p < 2 * R; ++p) {
-            const int d = R - 1 - p < 0 ? p + 1 - R : R - 1 - p;
+        for (int k = 0; k < K; ++k) {
 #pragma unroll
             for (int c = 0; c < C2; ++c) {
-                const float2 prev = p + 1 < 2 * R ? acc[p + 1][c] : make_float2(0.f, 0.f);
                 if (G::PACK) {
-                    acc[p][c] = __ffma2_rn(w2[d], hv[c], prev);
+                    out[k][c] = __ffma2_rn(make_float2(tp.w[R], tp.w[R]), hv[k][c], acc[0][c]);
                 } else {
-                    acc[p][c].x = fmaf(tp.w[d], hv[c].x, prev.x);
-                    acc[p][c].y = fmaf(tp.w[d], hv[c].y, prev.y);
+                    out[k][c].x = fmaf(tp.w[R], hv[k][c].x, acc[0][c].x);
+                    out[k][c].y = fmaf(tp.w[R], hv[k][c].y, acc[0][c].y);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 2 * R; ++p) {
+                const int d = R - 1 - p < 0 ? p + 1 - R : R - 1 - p;
+#pragma unroll
+                for (int c = 0; c < C2; ++c) {
+                    const float2 prev = p + 1 < 2 * R ? acc[p + 1][c] : make_float2(0.f, 0.f);
+                    if (G::PACK) {
+                        acc[p][c] = __ffma2_rn(make_float2(tp.w[d], tp.w[d]), hv[k][c], prev);
+                    } else {
+                        acc[p][c].x = fmaf(tp.w[d], hv[k][c].x, prev.x);
+                        acc[p][c].y = fmaf(tp.w[d], hv[k][c].y, prev.y);
+                    }
                 }
             }
         }
-        // ---- the row that just received its last term ----
-        const int y = i - R;
-        if (y >= fL && y <= eL) {
-            if (!LAST) {
-                float4* dst = reinterpret_cast<float4*>(ringL + out_off + x);
+        // ---- the rows that just received their last term ----
 #pragma unroll
-                for (int k = 0; k < C / 4; ++k)
-                    dst[k] = make_float4(out[2 * k].x, out[2 * k].y, out[2 * k + 1].x, out[2 * k + 1].y);
-            }
-            if (store_ok && y >= sc.y0 && y < sc.y1) {
-                const float4* cen = reinterpret_cast<const float4*>(ringP + cen_off + x + RA);
+        for (int k = 0; k < K; ++k) {
+            const int y = i + k - R;
+            if (y >= fL && y <= eL) {
+                if (!LAST) {
+                    float2* dst = reinterpret_cast<float2*>(ringL + out_off + x);
 #pragma unroll
-                for (int k = 0; k < C / 4; ++k) {
-                    if (gx + 4 * k >= w) break;
-                    const float4 ov = make_float4(out[2 * k].x, out[2 * k].y, out[2 * k + 1].x, out[2 * k + 1].y);
+                    for (int c = 0; c < C2; ++c) dst[c] = out[k][c];   // (pairs of STS.64 merge into STS.128)
+                }
+                if (store_ok && y >= sc.y0 && y < sc.y1) {
+                    const float2* cen = reinterpret_cast<const float2*>(ringP + cen_off + x + RA);
+                    if (C % 4 == 0) {
+#pragma unroll
+                        for (int q4 = 0; q4 < C / 4; ++q4) {
+                            if (gx + 4 * q4 >= w) break;
+                            const float4 ov = make_float4(out[k][2 * q4].x, out[k][2 * q4].y, out[k][2 * q4 + 1].x,
+                                                          out[k][2 * q4 + 1].y);
 #ifdef SB_EXP_NOSTG
-                    if (ov.x == 123.456f)
+                            if (ov.x == 123.456f)
 #endif
-                    if (gout != nullptr) *reinterpret_cast<float4*>(gout + e_off + 4 * k) = ov;
-                    if (dout != nullptr) {
-                        const float4 cv = cen[k];
+                            if (STORE_G) *reinterpret_cast<float4*>(gout + e_off + 4 * q4) = ov;
+                            {
+                                const float4 cv = *reinterpret_cast<const float4*>(cen + 2 * q4);
 #ifdef SB_EXP_NOSTG
-                        if (cv.x == 123.456f)
+                                if (cv.x == 123.456f)
 #endif
-                        *reinterpret_cast<float4*>(dout + e_off + 4 * k) =
-                            make_float4(ov.x - cv.x, ov.y - cv.y, ov.z - cv.z, ov.w - cv.w);
-                    }
-                    if (LAST && decp != nullptr && !(y & 1)) {
-                        const int dy = y >> 1, dx = (gx + 4 * k) >> 1;
-                        if (dy < a.dec_h) {
-                            if (dx + 1 < a.dec_w)
-                                *reinterpret_cast<float2*>(decp + (size_t)dy * a.dec_pitch + dx) =
-                                    make_float2(ov.x, ov.z);
-                            else if (dx < a.dec_w)
-                                decp[(size_t)dy * a.dec_pitch + dx] = ov.x;
+                                *reinterpret_cast<float4*>(dout + e_off + 4 * q4) =
+                                    make_float4(ov.x - cv.x, ov.y - cv.y, ov.z - cv.z, ov.w - cv.w);
+                            }
+                            if (LAST && decp != nullptr && !(y & 1)) {
+                                const int dy = y >> 1, dx = (gx + 4 * q4) >> 1;
+                                if (dy < a.dec_h) {
+                                    if (dx + 1 < a.dec_w)
+                                        *reinterpret_cast<float2*>(decp + (size_t)dy * a.dec_pitch + dx) =
+                                            make_float2(ov.x, ov.z);
+                                    else if (dx < a.dec_w)
+                                        decp[(size_t)dy * a.dec_pitch + dx] = ov.x;
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < C2; ++c) {
+                            if (gx + 2 * c >= w) break;
+                            const float2 ov = out[k][c];
+                            if (STORE_G) *reinterpret_cast<float2*>(gout + e_off + 2 * c) = ov;
+                            {
+                                const float2 cv = cen[c];
+                                *reinterpret_cast<float2*>(dout + e_off + 2 * c) = make_float2(ov.x - cv.x, ov.y - cv.y);
+                            }
+                            if (LAST && decp != nullptr && !(y & 1)) {
+                                const int dy = y >> 1, dx = (gx + 2 * c) >> 1;
+                                if (dy < a.dec_h && dx < a.dec_w) decp[(size_t)dy * a.dec_pitch + dx] = ov.x;
+                            }
                         }
                     }
                 }
             }
+            // ---- advance the per-row running state ----
+            cen_off += WP;
+            if (cen_off == DP * WP) cen_off = 0;
+            if (!LAST) {
+                out_off += WL;
+                if (out_off == DL * WL) out_off = 0;
+            }
+            e_off += (unsigned)a.pitch;
         }
-        // ---- advance the running state ----
-        if ((unsigned)i < (unsigned)(h - 1)) {   // rows above / below the image re-read the edge row
-            in_off += WP;
-            if (in_off == DP * WP) in_off = 0;
-        }
-        ++i;
-        cen_off += WP;
-        if (cen_off == DP * WP) cen_off = 0;
-        if (!LAST) {
-            out_off += WL;
-            if (out_off == DL * WL) out_off = 0;
-        }
-        e_off += (unsigned)a.pitch;
+        i += K;
     }
 }
 
-template <class G, bool BORDER>
+template <class G, bool BORDER, bool STORE_G>
 __device__ __forceinline__ void stream_body(const CascadeArgs& a, float* smem,
                                             const StreamSched& sc, int sx0) {
     const int warp = threadIdx.x >> 5;
     if (G::NL >= 3 && warp >= G::FIRSTWARP(3))
-        stream_level<G, (G::NL >= 3 ? 3 : 1), BORDER>(a, smem, threadIdx.x - 32 * G::FIRSTWARP(3), sc, sx0);
+        stream_level<G, (G::NL >= 3 ? 3 : 1), BORDER, STORE_G>(a, smem, threadIdx.x - 32 * G::FIRSTWARP(3), sc, sx0);
     else if (warp >= G::FIRSTWARP(2))
-        stream_level<G, 2, BORDER>(a, smem, threadIdx.x - 32 * G::FIRSTWARP(2), sc, sx0);
+        stream_level<G, 2, BORDER, STORE_G>(a, smem, threadIdx.x - 32 * G::FIRSTWARP(2), sc, sx0);
     else
-        stream_level<G, 1, BORDER>(a, smem, threadIdx.x, sc, sx0);
+        stream_level<G, 1, BORDER, STORE_G>(a, smem, threadIdx.x, sc, sx0);
 }
 
-// Schedule (per CTA, uniform).  Level l consumes virtual input row i_l(t) = i0[l] + (t - T[l]) at step t and
-// completes its row i_l(t) - R_l in the same step.  Level l starts the step after level l-1 completed the
-// first row level l reads, so from then on the row it needs was always completed one step earlier.  At the
-// top of the image i0[l] = -R_l: the level re-reads ring row 0 for R_l steps while its producer runs ahead,
-// hence ring depth 2 R_l + 2 (window row .. centre row of the DoG .. row being written); the input ring adds
-// the prefetch distance.
+// Schedule (per CTA, uniform), K rows per step.  Level l consumes the virtual input rows
+// i0[l] + K (t - T[l]) + k, k < K, at step t and completes the rows R_l above them in the same step.  Level l
+// starts the step after level l-1 completed the last row of level l's first step, so from then on the rows it
+// needs were always completed at least one step earlier.  At the top of the image i0[l] = -R_l: the level
+// re-reads ring row 0 while its producer runs ahead, hence ring depth 2 R_l + 3K - 1 (window rows .. centre row
+// of the DoG .. rows being written); the input ring adds the prefetch distance (K PF rows).
 // Work split: the (strip, row) space is flattened strip-major and cut into gridDim.x equal-cost ranges (a row of
 // a strip on the left / right image edge costs 3 units, an interior one 2: clamped window loads), so every CTA
 // gets the same amount of work whatever the image size; a range that crosses a strip boundary is run as two
 // (or more) passes of the pipeline.
-template <class G>
+// STORE_G: the level planes are stored (always for G1..G3; G4, G5 only for the debug planes); the DoG planes
+// always are.
+template <class G, bool STORE_G>
 __global__ void __launch_bounds__(G::THREADS, G::MINB) k_stream(const CascadeArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int strips = (a.w + G::WS - 1) / G::WS;
@@ -341,22 +378,23 @@ __global__ void __launch_bounds__(G::THREADS, G::MINB) k_stream(const CascadeArg
         sc.T[1] = 0;
 #pragma unroll
         for (int l = 1; l <= G::NL; ++l) {
-            sc.Tend[l] = sc.T[l] + (sc.e[l] + G::R(l) - sc.i0[l]);
-            if (l < G::NL) sc.T[l + 1] = sc.T[l] + 1 + G::R(l) + sc.f[l] - sc.i0[l];
+            sc.Tend[l] = sc.T[l] + (sc.e[l] + G::R(l) - sc.i0[l]) / G::K;
+            if (l < G::NL) sc.T[l + 1] = sc.T[l] + 1 + (sc.f[l] + G::K - 1 + G::R(l) - sc.i0[l]) / G::K;
         }
         sc.steps = sc.Tend[G::NL] + 1;
         if (border)
-            stream_body<G, true>(a, smem, sc, s * G::WS);
+            stream_body<G, true, STORE_G>(a, smem, sc, s * G::WS);
         else
-            stream_body<G, false>(a, smem, sc, s * G::WS);
+            stream_body<G, false, STORE_G>(a, smem, sc, s * G::WS);
     }
 }
 
 // default scale space (radii 4,5,6 | 8,10)
-// A: one warp per level (32 / 28 / 24 threads of 4 columns), 5 CTAs per SM (6 would cap the registers at 96 and
-// spill); B: two warps per level (64 / 58 threads), 3 CTAs per SM.  Measured alternatives in DESIGN.md.
-using StreamA = StreamGeom<3, 4, 5, 6, 4, 96, 12, 5, true>;    // G0 -> G1,G2,G3, D0,D1,D2, next base
-using StreamB = StreamGeom<2, 8, 10, 0, 4, 232, 12, 3, true>;  // G3 -> (G4,G5) -> D3,D4
+// A: one warp per level (32 / 28 / 24 threads of 4 columns), one row per step, 5 CTAs per SM (6 would cap the
+// registers at 96 and spill); B: two warps per level (64 / 58 threads), two rows per step (half the barriers,
+// two independent rows in the horizontal pass), 3 CTAs per SM.  Measured alternatives in DESIGN.md.
+using StreamA = StreamGeom<3, 4, 5, 6, 4, 96, 12, 5, true, 1>;    // G0 -> G1,G2,G3, D0,D1,D2, next base
+using StreamB = StreamGeom<2, 8, 10, 0, 4, 232, 6, 3, true, 2>;   // G3 -> (G4,G5) -> D3,D4
 
 template <class G>
 cudaError_t launch_stream_t(const CascadeArgs& a, int sm_count, cudaStream_t s, int force_ctas = 0) {
@@ -367,6 +405,11 @@ cudaError_t launch_stream_t(const CascadeArgs& a, int sm_count, cudaStream_t s, 
     int ctas = sm_count * G::MINB;
     if (units < ctas) ctas = (int)units;
     if (force_ctas > 0) ctas = force_ctas;
-    k_stream<G><<<ctas, G::THREADS, G::kSmem, s>>>(a);
+    for (int l = 0; l < G::NL; ++l)
+        if (a.d[l] == nullptr || (a.g[l] == nullptr) != (a.g[0] == nullptr)) return cudaErrorInvalidValue;
+    if (a.g[0] != nullptr)
+        k_stream<G, true><<<ctas, G::THREADS, G::kSmem, s>>>(a);
+    else
+        k_stream<G, false><<<ctas, G::THREADS, G::kSmem, s>>>(a);
     return cudaGetLastError();
 }
