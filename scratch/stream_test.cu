@@ -136,7 +136,10 @@ static void time_size(int w, int h) {
         }
         printf("  tile cascade %c: %7.1f us\n", variant ? 'B' : 'A', best * 1e3);
     }
-    time_variant<StreamA, StreamB>("stream A(4col,96) B(4col,104) 6/6", p, w, h, pitch, 0);
+    time_variant<StreamA, StreamB>("stream default (auto split)", p, w, h, pitch, 0);
+    time_variant<StreamA, StreamB>("stream default, flattened split", p, w, h, pitch, 1);
+    time_variant<StreamA, StreamB>("stream default, 8 bands", p, w, h, pitch, -8);
+    time_variant<StreamA, StreamB>("stream default, 12 bands", p, w, h, pitch, -12);
     using A_k2 = StreamGeom<3, 4, 5, 6, 4, 96, 6, 4, true, 2>;
     using B_k1 = StreamGeom<2, 8, 10, 0, 4, 232, 12, 3, true, 1>;
     time_variant<A_k2, B_k1>("A K=2 4/SM PF6, B(232) K=1 PF12", p, w, h, pitch, 0);
@@ -187,7 +190,8 @@ int run(int argc, char** argv) {
     }
     int fails = 0;
     const int sizes[][3] = {{40, 30, 0}, {230, 50, 0}, {300, 200, 0}, {300, 200, 3}, {1000, 700, 0}, {1000, 700, 5},
-                            {225, 131, 2}, {7, 9, 0}, {1, 1, 0}, {2, 300, 4}, {960, 540, 0}, {1920, 1080, 0}, {449, 64, 1}};
+                            {225, 131, 2}, {7, 9, 0}, {1, 1, 0}, {2, 300, 4}, {960, 540, 0}, {1920, 1080, 0}, {449, 64, 1},
+                            {300, 200, -3}, {1000, 700, -2}, {225, 131, -1}, {2, 300, -4}, {7, 9, -2}, {100, 500, -7}};
 #ifndef QUICK
     for (auto& s : sizes) { fails += check(s[0], s[1], s[2], false); fails += check(s[0], s[1], s[2], true); }
 #endif

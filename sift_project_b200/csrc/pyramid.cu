@@ -8,6 +8,7 @@
 //
 // HBM-bound by design: one read of G[i-1], one write of G[i], one write of D[i-1] per level.
 #include <cstdlib>
+#include <type_traits>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -625,14 +626,14 @@ bool cascade_supported(const BlurTaps* taps) {
 cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, float* dec, int dec_w, int dec_h,
                                 int dec_pitch, bool keep_all, int sm_count, int mode, int part, cudaStream_t s) {
     // Measured on B200.  Alone on the GPU (scratch/stream_test.cu): 7680 x 4320 tile 303 + 249 us, streaming
-    // 261 + 214 us; 3840 x 2160 equal (170 us); below that the tile kernels are faster (the pipeline fill of
-    // ~35 rows per CTA is pure latency).  With four images in flight the streaming kernels (small CTAs, 24-55 KB
-    // of shared memory) share the SMs better with the other images' kernels: 4K batch images/s by threshold
-    // 20 Mpx 548, 8 Mpx 552, 2 Mpx 563, 0.5 Mpx 562, all octaves 555 against 511 with tile kernels only, while
-    // the single-image pyramid time goes 0.869 / 0.874 / 0.910 / 0.963 / 1.27 ms.  8 Mpx keeps both.
+    // 232 + 166 us; 3840 x 2160 tile 94 + 76 us, streaming 74 + 72 us; below ~2 Mpx the tile kernels are faster
+    // alone (the pipeline fill of ~35 rows per CTA is pure latency).  With four images in flight the streaming
+    // kernels (small CTAs, 24-62 KB of shared memory) also share the SMs better with the other images' kernels:
+    // 4K batch images/s by threshold 8 Mpx 580, 2 Mpx 594, 0.5 Mpx 590 against 511 with tile kernels only,
+    // single-image pyramid time 0.762 / 0.789 / 0.834 ms against 0.943.
     // SIFT_B200_STREAM_MIN_PX overrides the threshold (experiments).
     static const long long min_px =
-        getenv("SIFT_B200_STREAM_MIN_PX") ? atoll(getenv("SIFT_B200_STREAM_MIN_PX")) : 8000000ll;
+        getenv("SIFT_B200_STREAM_MIN_PX") ? atoll(getenv("SIFT_B200_STREAM_MIN_PX")) : 2000000ll;
     const bool stream = mode == 3 || (mode == 0 && (long long)od.w * od.h >= min_px);
     CascadeArgs a;
     a.in = od.G[0];

@@ -165,14 +165,19 @@ __device__ __forceinline__ void stream_level(const CascadeArgs& a, float* smem, 
         for (int g = 0; g < G::PF; ++g) fetch.next();
     }
 
-#pragma unroll 1
-    for (int t = 0; t < steps; ++t) {
-        if (L == 1) {
-            fetch.next();
-            stream_wait<G::PF>();
-        }
-        stream_bar();
-        if (t < T || t > Tend) continue;   // pipeline fill / drain: this level has nothing to do
+    // Steady steps: the level is active, every row it reads is inside the image (no clamping) and every row it
+    // completes is stored; the step body is instantiated without those tests for them.
+    int ts_lo, ts_hi;
+    {
+        auto cdiv = [](int n, int d) { return n >= 0 ? (n + d - 1) / d : -((-n) / d); };
+        auto fdiv = [](int n, int d) { return n >= 0 ? n / d : -((-n + d - 1) / d); };
+        const int ylo = max(fL, sc.y0), yhi = min(eL, sc.y1 - 1);
+        ts_lo = T + max(max(cdiv(-i0, K), cdiv(ylo + R - i0, K)), 0);
+        ts_hi = min(T + min(fdiv(h - 2 - (K - 1) - i0, K), fdiv(yhi + R - (K - 1) - i0, K)), Tend);
+    }
+    auto step = [&](const int t, auto steady_tag) {
+        constexpr bool STEADY = decltype(steady_tag)::value;
+        if (!STEADY && (t < T || t > Tend)) return;   // pipeline fill / drain: this level has nothing to do
         // ---- horizontal pass of K rows: C outputs each from a register window ----
         float2 hv[K][C2];
 #pragma unroll
@@ -209,7 +214,7 @@ __device__ __forceinline__ void stream_level(const CascadeArgs& a, float* smem, 
                 const float o = fmaf(tp.w[0], v[RA + c], sacc);
                 if (c & 1) hv[k][c / 2].y = o; else hv[k][c / 2].x = o;
             }
-            if ((unsigned)(i + k) < (unsigned)(h - 1)) {   // rows above / below the image re-read the edge row
+            if (STEADY || (unsigned)(i + k) < (unsigned)(h - 1)) {   // rows above / below the image re-read the edge row
                 in_off += WP;
                 if (in_off == DP * WP) in_off = 0;
             }
@@ -249,13 +254,13 @@ __device__ __forceinline__ void stream_level(const CascadeArgs& a, float* smem, 
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int y = i + k - R;
-            if (y >= fL && y <= eL) {
+            if (STEADY || (y >= fL && y <= eL)) {
                 if (!LAST) {
                     float2* dst = reinterpret_cast<float2*>(ringL + out_off + x);
 #pragma unroll
                     for (int c = 0; c < C2; ++c) dst[c] = out[k][c];   // (pairs of STS.64 merge into STS.128)
                 }
-                if (store_ok && y >= sc.y0 && y < sc.y1) {
+                if (store_ok && (STEADY || (y >= sc.y0 && y < sc.y1))) {
                     const float2* cen = reinterpret_cast<const float2*>(ringP + cen_off + x + RA);
                     if (C % 4 == 0) {
 #pragma unroll
@@ -314,6 +319,29 @@ __device__ __forceinline__ void stream_level(const CascadeArgs& a, float* smem, 
             e_off += (unsigned)a.pitch;
         }
         i += K;
+    };
+    auto sync_step = [&]() {
+        if (L == 1) {
+            fetch.next();
+            stream_wait<G::PF>();
+        }
+        stream_bar();
+    };
+    int t = 0;
+#pragma unroll 1
+    for (; t < min(ts_lo, steps); ++t) {
+        sync_step();
+        step(t, std::false_type{});
+    }
+#pragma unroll 1
+    for (; t <= min(ts_hi, steps - 1); ++t) {
+        sync_step();
+        step(t, std::true_type{});
+    }
+#pragma unroll 1
+    for (; t < steps; ++t) {
+        sync_step();
+        step(t, std::false_type{});
     }
 }
 
@@ -335,20 +363,43 @@ __device__ __forceinline__ void stream_body(const CascadeArgs& a, float* smem,
 // needs were always completed at least one step earlier.  At the top of the image i0[l] = -R_l: the level
 // re-reads ring row 0 while its producer runs ahead, hence ring depth 2 R_l + 3K - 1 (window rows .. centre row
 // of the DoG .. rows being written); the input ring adds the prefetch distance (K PF rows).
-// Work split: the (strip, row) space is flattened strip-major and cut into gridDim.x equal-cost ranges (a row of
-// a strip on the left / right image edge costs 3 units, an interior one 2: clamped window loads), so every CTA
-// gets the same amount of work whatever the image size; a range that crosses a strip boundary is run as two
-// (or more) passes of the pipeline.
+// Work split, two forms.  nseg == 0 (any image size): the (strip, row) space is flattened strip-major and cut into
+// gridDim.x equal-cost ranges (a row of a strip on the left / right image edge costs 3 units, an interior one 2:
+// clamped window loads), so every CTA gets the same amount of work; a range that crosses a strip boundary is
+// run as two (or more) passes of the pipeline.  nseg > 0 (when strips x nseg fills the GPU): every strip is cut
+// into the same nseg row bands (2 nseg half-height ones for an edge strip), one CTA each: the CTAs of a band walk
+// down the same rows at the same time, so a plane row is written as one run across the strips (DRAM pages,
+// and the x-halo reads of the neighbours hit L2).
 // STORE_G: the level planes are stored (always for G1..G3; G4, G5 only for the debug planes); the DoG planes
 // always are.
 template <class G, bool STORE_G>
-__global__ void __launch_bounds__(G::THREADS, G::MINB) k_stream(const CascadeArgs a) {
+__global__ void __launch_bounds__(G::THREADS, G::MINB) k_stream(const CascadeArgs a, const int nseg) {
     extern __shared__ __align__(16) float smem[];
     const int strips = (a.w + G::WS - 1) / G::WS;
     auto is_border = [&](int s) { return s * G::WS - G::HO(0) < 0 || s * G::WS + G::WS + G::HO(0) > a.w; };
-    long long total = 0;
-    for (int s = 0; s < strips; ++s) total += (long long)a.h * (is_border(s) ? 3 : 2);
-    const long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
+    long long lo, hi;
+    if (nseg == 0) {
+        long long total = 0;
+        for (int s = 0; s < strips; ++s) total += (long long)a.h * (is_border(s) ? 3 : 2);
+        lo = total * blockIdx.x / gridDim.x;
+        hi = total * (blockIdx.x + 1) / gridDim.x;
+    } else {
+        int k = blockIdx.x, s = 0;
+        long long off = 0;
+        for (; s < strips; ++s) {
+            const int n = is_border(s) ? 2 * nseg : nseg;
+            if (k < n) break;
+            k -= n;
+            off += (long long)a.h * (is_border(s) ? 3 : 2);
+        }
+        if (s == strips) return;
+        const int c = is_border(s) ? 3 : 2, n = is_border(s) ? 2 * nseg : nseg;
+        const int hs = (a.h + n - 1) / n;
+        const int y0 = k * hs, y1 = min(y0 + hs, a.h);
+        if (y0 >= y1) return;
+        lo = off + (long long)y0 * c;
+        hi = off + (long long)y1 * c;
+    }
     long long beg = 0;
     bool first = true;
     for (int s = 0; s < strips; ++s) {
@@ -397,19 +448,30 @@ using StreamA = StreamGeom<3, 4, 5, 6, 4, 96, 12, 5, true, 1>;    // G0 -> G1,G2
 using StreamB = StreamGeom<2, 8, 10, 0, 4, 232, 6, 3, true, 2>;   // G3 -> (G4,G5) -> D3,D4
 
 template <class G>
-cudaError_t launch_stream_t(const CascadeArgs& a, int sm_count, cudaStream_t s, int force_ctas = 0) {
+cudaError_t launch_stream_t(const CascadeArgs& a, int sm_count, cudaStream_t s, int force = 0) {
     const int strips = (a.w + G::WS - 1) / G::WS;
-    // one wave of CTAs, fewer when the image is too small to give each of them min_rows rows
+    const int slots = sm_count * G::MINB;   // one wave of CTAs
+    int nb = 0;                             // strips on an image edge
+    for (int t = 0; t < strips; ++t) nb += t * G::WS - G::HO(0) < 0 || t * G::WS + G::WS + G::HO(0) > a.w;
+    // aligned row bands when they fill >= 90 % of the wave with bands of >= 96 rows, else the flattened split
+    // (fewer CTAs when the image is too small to give each of them min_rows rows)
     const int min_rows = 48;
-    const long long units = ((long long)strips * a.h + min_rows - 1) / min_rows;
-    int ctas = sm_count * G::MINB;
-    if (units < ctas) ctas = (int)units;
-    if (force_ctas > 0) ctas = force_ctas;
+    int nseg = slots / (strips + nb), ctas;
+    if (nseg < 1 || (strips + nb) * nseg * 10 < slots * 9 || a.h / nseg < 96) nseg = 0;
+    if (force < 0) nseg = -force;   // experiments: 1 = flattened, > 1 = flattened with that many CTAs, < 0 = -force bands
+    if (force > 0) nseg = 0;
+    if (nseg > 0) {
+        ctas = (strips + nb) * nseg;
+    } else {
+        const long long units = ((long long)strips * a.h + min_rows - 1) / min_rows;
+        ctas = units < slots ? (int)units : slots;
+        if (force > 1) ctas = force;
+    }
     for (int l = 0; l < G::NL; ++l)
         if (a.d[l] == nullptr || (a.g[l] == nullptr) != (a.g[0] == nullptr)) return cudaErrorInvalidValue;
     if (a.g[0] != nullptr)
-        k_stream<G, true><<<ctas, G::THREADS, G::kSmem, s>>>(a);
+        k_stream<G, true><<<ctas, G::THREADS, G::kSmem, s>>>(a, nseg);
     else
-        k_stream<G, false><<<ctas, G::THREADS, G::kSmem, s>>>(a);
+        k_stream<G, false><<<ctas, G::THREADS, G::kSmem, s>>>(a, nseg);
     return cudaGetLastError();
 }

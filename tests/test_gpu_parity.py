@@ -368,7 +368,7 @@ def test_fused_octave_cascade_equals_per_level_kernels(ctx):
 
 
 def test_streaming_cascade_on_a_large_octave():
-    """Default mode at a size where octave 0 takes the streaming kernels (>= 8 Mpx) and the rest the tile
+    """Default mode at a size where octave 0 takes the streaming kernels (>= 2 Mpx) and the rest the tile
     kernels: same bytes as tile kernels everywhere and as streaming kernels everywhere, without the debug
     planes (G4, G5 stay on chip).  Width 3000 -> base 6000 x 3600: strips of 96 / 232 columns do not divide it."""
     img = O.synth_image(1800, 3000, seed=11)
