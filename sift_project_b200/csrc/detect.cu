@@ -291,10 +291,10 @@ k_refine(const PyramidDesc* __restrict__ pyr, const Cand* __restrict__ cands, Kp
 constexpr int ORI_COPIES = 8;
 constexpr int kMaxOriBins = 128;   // largest num_bins of the generic instantiation
 
-// NB > 0: compile-time bin count (36, the reference default: smoothing stays in registers);
-// NB == 0: sp.num_bins at run time (<= kMaxOriBins), smoothing through shared memory.
+// NB > 0: compile-time bin count (36, the reference default); NB == 0: sp.num_bins at run time
+// (<= kMaxOriBins).  The sequential smoothing runs through shared memory in both.
 template <int NB>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 4)
 k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, KpCore* __restrict__ oriented,
          Counters* __restrict__ counters, const StageParams sp) {
     constexpr int CAPB = NB > 0 ? NB : kMaxOriBins;
@@ -357,32 +357,28 @@ k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, Kp
         // bin i sees the already-updated bin i-1, and the last bin the already-updated bin 0); with
         // a compile-time bin count the loop is fully unrolled and the values stay in registers.
         // All lanes then test their bins for peaks.
+        for (int b = lane; b < nb; b += 32) {
+            unsigned long long t = 0;
+#pragma unroll
+            for (int cpy = 0; cpy < COPIES; ++cpy) t += hist[cpy * CAPB + b];
+            smooth[b] = (double)t * unfix;
+        }
+        __syncwarp();
         if (lane == 0) {
-            if (NB > 0) {
-                double hd[CAPB];
-#pragma unroll
-                for (int b = 0; b < CAPB; ++b) {
-                    unsigned long long t = 0;
-#pragma unroll
-                    for (int cpy = 0; cpy < COPIES; ++cpy) t += hist[cpy * CAPB + b];
-                    hd[b] = (double)t * unfix;
+            // a sliding window of three values in registers, the rest in shared memory: the 36 doubles of the
+            // histogram would otherwise cost 72 registers per thread and halve the occupancy of the sample loop
+#pragma unroll 1
+            for (int it = 0; it < 2; ++it) {  // ORI_SMOOTH_ITERATIONS
+                double prev = smooth[nb - 1], cur = smooth[0];
+#pragma unroll 6
+                for (int b = 0; b + 1 < nb; ++b) {
+                    const double nxt = smooth[b + 1];
+                    const double v = 0.25 * prev + 0.5 * cur + 0.25 * nxt;
+                    smooth[b] = v;
+                    prev = v;
+                    cur = nxt;
                 }
-#pragma unroll
-                for (int it = 0; it < 2; ++it)  // ORI_SMOOTH_ITERATIONS
-#pragma unroll
-                    for (int b = 0; b < CAPB; ++b)
-                        hd[b] = 0.25 * hd[(b + CAPB - 1) % CAPB] + 0.5 * hd[b] + 0.25 * hd[(b + 1) % CAPB];
-#pragma unroll
-                for (int b = 0; b < CAPB; ++b) smooth[b] = hd[b];
-            } else {
-                for (int b = 0; b < nb; ++b) {
-                    unsigned long long t = 0;
-                    for (int cpy = 0; cpy < COPIES; ++cpy) t += hist[cpy * CAPB + b];
-                    smooth[b] = (double)t * unfix;
-                }
-                for (int it = 0; it < 2; ++it)
-                    for (int b = 0; b < nb; ++b)
-                        smooth[b] = 0.25 * smooth[(b + nb - 1) % nb] + 0.5 * smooth[b] + 0.25 * smooth[(b + 1) % nb];
+                smooth[nb - 1] = 0.25 * prev + 0.5 * cur + 0.25 * smooth[0];
             }
         }
         __syncwarp();
