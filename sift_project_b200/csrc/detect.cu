@@ -569,10 +569,15 @@ __global__ void __launch_bounds__(256) k_bucket_gather(SortScratch ss) {
 // ------------------------------------------------------------------------------------------
 constexpr int DESC_COPIES = 2;   // odd / even lanes (8 copies x 4 warps measured slower: occupancy)
 constexpr int DESC_WARPS = 8;    // warps (= keypoints in flight) per CTA
+#ifndef SB_DESC_CTAS
+#define SB_DESC_CTAS 5
+#endif
+constexpr int DESC_CTAS = SB_DESC_CTAS;   // CTAs per SM (the grid is exactly one wave).  4 (64 registers) 0.492 ms,
+                                          // 5 (48 registers, 8 B spilled) 0.461 ms, 6 (40 registers) 0.459 ms
 constexpr int DESC_GRID = 6;                            // 4x4 cells + a one-cell border that absorbs dropped bins
 constexpr int DESC_WORDS = DESC_GRID * DESC_GRID * 8;   // per histogram copy
 
-__global__ void __launch_bounds__(DESC_WARPS * 32)
+__global__ void __launch_bounds__(DESC_WARPS * 32, DESC_CTAS)
 k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ oriented,
            const int* __restrict__ final_order, Counters* __restrict__ counters,
            uint8_t* __restrict__ records, uint8_t* __restrict__ desc, int cap_final, const StageParams sp) {
@@ -809,7 +814,7 @@ cudaError_t launch_sort_dedup(const KpCore* oriented, Counters* counters, const 
 cudaError_t launch_describe(const PyramidDesc* d_pyr, const KpCore* oriented, const int* final_order,
                             Counters* counters, uint8_t* records, uint8_t* desc, int cap_final,
                             const StageParams& sp, cudaStream_t s) {
-    k_describe<<<148 * 4, DESC_WARPS * 32, 0, s>>>(d_pyr, oriented, final_order, counters, records, desc, cap_final, sp);
+    k_describe<<<148 * DESC_CTAS, DESC_WARPS * 32, 0, s>>>(d_pyr, oriented, final_order, counters, records, desc, cap_final, sp);
     return cudaGetLastError();
 }
 
