@@ -416,12 +416,17 @@ __global__ void __launch_bounds__(NTP, MINB) k_cascade(const CascadeArgs a) {
 template <int R1, int R2, int R3>
 cudaError_t launch_cascade_t(const CascadeArgs& a, int sm_count, cudaStream_t s) {
     const int big_tiles = ((a.w + CTW - 1) / CTW) * ((a.h + TH - 1) / TH);
+    const int small_tiles = ((a.w + 31) / 32) * ((a.h + 31) / 32);
     if (big_tiles >= 2 * sm_count) {
         dim3 grid((a.w + CTW - 1) / CTW, (a.h + TH - 1) / TH);
         k_cascade<R1, R2, R3, CTW, TH, CCT, 2><<<grid, CCT, CascadeGeom<R1, R2, R3, CTW, TH>::kSmem, s>>>(a);
-    } else {
+    } else if (small_tiles > sm_count) {
         dim3 grid((a.w + 31) / 32, (a.h + 31) / 32);
         k_cascade<R1, R2, R3, 32, 32, 128, 4><<<grid, 128, CascadeGeom<R1, R2, R3, 32, 32>::kSmem, s>>>(a);
+    } else {
+        // at most one tile per SM: the kernel time is one tile's serial phases, so spread each over 512 threads
+        dim3 grid((a.w + 31) / 32, (a.h + 31) / 32);
+        k_cascade<R1, R2, R3, 32, 32, 512, 1><<<grid, 512, CascadeGeom<R1, R2, R3, 32, 32>::kSmem, s>>>(a);
     }
     return cudaGetLastError();
 }
@@ -573,6 +578,7 @@ cudaError_t pyramid_init() {
                                   (int)CascadeGeom<R1, R2, R3, TWP, THP>::kSmem)) != cudaSuccess) return e;
     SB_CASC_ATTR(4, 5, 6, CTW, TH, CCT, 2) SB_CASC_ATTR(8, 10, 0, CTW, TH, CCT, 2)
     SB_CASC_ATTR(4, 5, 6, 32, 32, 128, 4) SB_CASC_ATTR(8, 10, 0, 32, 32, 128, 4)
+    SB_CASC_ATTR(4, 5, 6, 32, 32, 512, 1) SB_CASC_ATTR(8, 10, 0, 32, 32, 512, 1)
 #undef SB_CASC_ATTR
 #define SB_STREAM_ATTR(G, SG)                                                                              \
     if ((e = cudaFuncSetAttribute(k_stream<G, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmem)) != \
