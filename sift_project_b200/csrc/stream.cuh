@@ -4,17 +4,17 @@
 // Same arithmetic as k_cascade / k_blur (image.cpp:156-238 per level, subtract image.cpp:30-36, nearest
 // decimation image.cpp:41-55), bit-identical results, different data movement:
 //
-//   * a CTA owns a column strip of WS outputs and a segment of rows and walks DOWN the rows, one row per
-//     step; there is no y halo to recompute (only a warm-up of sum(R) rows per segment) and no 2-D tile
-//     passing through shared memory in barrier-separated passes;
+//   * a CTA owns a column strip of WS outputs and a band of rows and walks DOWN the rows, K rows per step;
+//     there is no y halo to recompute (only a pipeline fill of sum(R) rows per CTA) and no 2-D tile passing
+//     through shared memory in barrier-separated passes;
 //   * the levels of the cascade form a pipeline over shared-memory row rings: the warps of level l read
-//     the row that level l-1 completed in the previous step, so one CTA barrier per row step is enough;
-//   * per step a thread of level l (C adjacent columns) runs the horizontal pass of ONE row from a
-//     register window (C + 2R floats, vector LDS) and then the vertical pass in SCATTER form: the new
-//     horizontal value is accumulated into the 2R+1 output rows it contributes to, which live in
-//     registers ((2R+1) x C rotating accumulators, rotation resolved at compile time by unrolling the
-//     step loop 2R+1 times).  Each accumulator receives its terms in ascending input-row order starting
-//     from fma(w[R], v, 0) -- exactly the order of cascade_vpass -- so the sums round identically;
+//     the rows that level l-1 completed in the previous step, so one CTA barrier per step is enough;
+//   * per row a thread of level l (C adjacent columns) runs the horizontal pass from a register window
+//     (C + 2R floats, vector LDS) and then the vertical pass in SCATTER form: the new horizontal value is
+//     accumulated into the 2R+1 output rows it contributes to, which live in registers (2R x C accumulators
+//     that move down one slot per row through the FMA itself: destination slot p, addend slot p+1).  Each
+//     accumulator receives its terms in ascending input-row order starting from fma(w[R], v, 0) -- exactly
+//     the order of cascade_vpass -- so the sums round identically;
 //   * the row that completes is written to the level's ring (next level's input) and, inside the
 //     strip, straight from registers to HBM together with its DoG against the previous level's row.
 //
@@ -24,6 +24,7 @@
 // Clamp-to-edge semantics of every level: rows outside the image are read as the edge row of the ring
 // (virtual row index clamped); columns outside the image are read with clamped column indices in the
 // strips that touch the left / right image edge (BORDER variant of the window load).
+// Design history, measurements and the variants that lost: DESIGN.md, "Streaming cascade".
 
 struct StreamSched {
     int y0, y1;            // output rows [y0, y1) of the last level

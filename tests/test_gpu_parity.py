@@ -367,6 +367,24 @@ def test_fused_octave_cascade_equals_per_level_kernels(ctx):
     ctx.debug_options()
 
 
+def test_profile_marks_add_up_to_the_stage_profile(ctx):
+    """sift_b200_get_profile_marks is the unaggregated form of sift_b200_get_profile: same stages, same total
+    time, the fused pyramid bracketed kernel by kernel on octave 0 and per octave below."""
+    img = O.synth_image(300, 400, seed=5)
+    ctx.set_profiling(True)
+    ctx.detect(img)
+    ms, nl = ctx.profile()
+    marks = ctx.profile_marks()
+    ctx.set_profiling(False)
+    octs = ctx.stats()["octaves"]
+    assert [st for st, _ in marks][:4] == ["input", "pyramid", "pyramid", "extrema"]
+    assert sum(1 for st, _ in marks if st == "pyramid") == octs + 1
+    assert nl["pyramid"] == 2 * octs
+    for st in S.SiftContext.STAGES:
+        assert abs(sum(t for s_, t in marks if s_ == st) - ms[st]) < 1e-3, st
+    assert all(t >= 0 for _, t in marks)
+
+
 def test_streaming_cascade_on_a_large_octave():
     """Default mode at a size where octave 0 takes the streaming kernels (>= 2 Mpx) and the rest the tile
     kernels: same bytes as tile kernels everywhere and as streaming kernels everywhere, without the debug
