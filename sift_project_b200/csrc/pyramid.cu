@@ -440,13 +440,19 @@ cudaError_t launch_cascade_t(const CascadeArgs& a, int sm_count, cudaStream_t s)
 // is written.  Reads 1 byte, writes 16 bytes per input pixel instead of 4 + 32 + 16.
 // ------------------------------------------------------------------------------------------
 constexpr int IN_R = 4;
-constexpr int IN_W0 = TW + 2 * IN_R, IN_H0 = TH + 2 * IN_R;
-constexpr size_t kInputSmem = (size_t)(IN_W0 * IN_H0 + TW * IN_H0) * sizeof(float);
+template <int TWI, int THI>
+struct InputGeom {
+    static constexpr int W0 = TWI + 2 * IN_R, H0 = THI + 2 * IN_R;
+    static constexpr size_t kSmem = (size_t)(W0 * H0 + TWI * H0) * sizeof(float);
+};
 
-template <bool DOUBLED>
-__global__ void __launch_bounds__(CT, 2)
+// TWI x THI = output tile, NTI = threads, MINBI = CTAs per SM
+template <bool DOUBLED, int TWI, int THI, int NTI, int MINBI>
+__global__ void __launch_bounds__(NTI, MINBI)
 k_input_u8(const uint8_t* __restrict__ src, int sw, int sh, float* __restrict__ dst, int w, int h, int pitch,
            const BlurTaps taps) {
+    constexpr int IN_W0 = InputGeom<TWI, THI>::W0, IN_H0 = InputGeom<TWI, THI>::H0;
+    constexpr int TW = TWI, TH = THI, CT = NTI;
     extern __shared__ __align__(16) float smem[];
     float* sA = smem;
     float* sT = smem + IN_W0 * IN_H0;
@@ -568,10 +574,10 @@ cudaError_t init_blur_r() {
 // Per-device one-time setup (opt-in to > 48 KB dynamic shared memory); called by context creation.
 cudaError_t pyramid_init() {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_input_u8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)kInputSmem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_input_u8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)kInputSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_input_u8<true, 128, 32, 512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)InputGeom<128, 32>::kSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_input_u8<false, 128, 32, 512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)InputGeom<128, 32>::kSmem)) != cudaSuccess) return e;
 #define SB_CASC_ATTR(R1, R2, R3, TWP, THP, NTP, MINB)                                                       \
     if ((e = cudaFuncSetAttribute(k_cascade<R1, R2, R3, TWP, THP, NTP, MINB>,                             \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
@@ -611,11 +617,13 @@ bool input_fused_supported(int channels, const BlurTaps& taps) { return channels
 
 cudaError_t launch_input_u8(const uint8_t* src, int sw, int sh, float* dst, int w, int h, int pitch, int doubled,
                             const BlurTaps& taps, cudaStream_t s) {
-    dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH);
+    // tile shapes measured at 4K (ms): 128x64 / 512 threads / 2 per SM 0.088, 128x32 / 256 / 4 0.079,
+    // 128x32 / 512 / 3 0.077, 64x64 / 256 / 4 0.077, 128x16 / 256 / 6 0.078
+    dim3 grid((w + 127) / 128, (h + 31) / 32);
     if (doubled)
-        k_input_u8<true><<<grid, CT, kInputSmem, s>>>(src, sw, sh, dst, w, h, pitch, taps);
+        k_input_u8<true, 128, 32, 512, 3><<<grid, 512, InputGeom<128, 32>::kSmem, s>>>(src, sw, sh, dst, w, h, pitch, taps);
     else
-        k_input_u8<false><<<grid, CT, kInputSmem, s>>>(src, sw, sh, dst, w, h, pitch, taps);
+        k_input_u8<false, 128, 32, 512, 3><<<grid, 512, InputGeom<128, 32>::kSmem, s>>>(src, sw, sh, dst, w, h, pitch, taps);
     return cudaGetLastError();
 }
 
