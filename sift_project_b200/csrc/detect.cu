@@ -97,8 +97,13 @@ __device__ __noinline__ void extrema_emit(unsigned m, bool hit, int lane, int x,
 
 // EX_ROWS = output rows per warp: 32 on large octaves (2 halo rows per 32), 8 on small ones, where the
 // grid would otherwise not fill the GPU and a warp's serial walk down 34 rows is pure latency
+// CTAs per SM: 3 (85 registers, no spills) 0.412 ms at 4K, 4 (64 registers, spills in the row loop) 0.431 ms,
+// 5 0.561 ms
+#ifndef SB_EXT_CTAS
+#define SB_EXT_CTAS 3
+#endif
 template <int EX_ROWS, int ND>   // ND = DoG planes per octave (intervals + 2); planes 1 .. ND-2 are tested
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, SB_EXT_CTAS)
 k_extrema(const OctaveDesc oct, int octave, float thr, Cand* __restrict__ cands, int cap,
           Counters* __restrict__ counters) {
     const unsigned FULL = 0xffffffffu;
@@ -293,8 +298,12 @@ constexpr int kMaxOriBins = 128;   // largest num_bins of the generic instantiat
 
 // NB > 0: compile-time bin count (36, the reference default); NB == 0: sp.num_bins at run time
 // (<= kMaxOriBins).  The sequential smoothing runs through shared memory in both.
+// CTAs per SM (the grid is exactly one wave): 4 0.099 ms at 4K, 5 0.091 ms, 6 0.090 ms
+#ifndef SB_ORI_CTAS
+#define SB_ORI_CTAS 5
+#endif
 template <int NB>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, SB_ORI_CTAS)
 k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, KpCore* __restrict__ oriented,
          Counters* __restrict__ counters, const StageParams sp) {
     constexpr int CAPB = NB > 0 ? NB : kMaxOriBins;
@@ -790,9 +799,9 @@ cudaError_t launch_refine(const PyramidDesc* d_pyr, const Cand* cands, KpCore* r
 cudaError_t launch_orient(const PyramidDesc* d_pyr, const KpCore* raw, KpCore* oriented, Counters* counters,
                           const StageParams& sp, cudaStream_t s) {
     if (sp.num_bins == kOriBins)
-        k_orient<kOriBins><<<148 * 4, 256, 0, s>>>(d_pyr, raw, oriented, counters, sp);
+        k_orient<kOriBins><<<148 * SB_ORI_CTAS, 256, 0, s>>>(d_pyr, raw, oriented, counters, sp);
     else
-        k_orient<0><<<148 * 4, 256, 0, s>>>(d_pyr, raw, oriented, counters, sp);
+        k_orient<0><<<148 * SB_ORI_CTAS, 256, 0, s>>>(d_pyr, raw, oriented, counters, sp);
     return cudaGetLastError();
 }
 
