@@ -119,9 +119,9 @@ k_extrema(const OctaveDesc oct, int octave, float thr, Cand* __restrict__ cands,
     float hmin[ND][3], hmax[ND][3], ctr[ND - 2][3];
     float raw[3][ND];  // rows loaded two iterations ahead of their use (bytes in flight hide HBM latency)
     auto fetch = [&](int y, int rs) {
-        const int yc = min(y, h - 1);
+        const unsigned off = (unsigned)min(y, h - 1) * (unsigned)pitch + (unsigned)xc;   // a plane has < 2^32 pixels
 #pragma unroll
-        for (int z = 0; z < ND; ++z) raw[rs][z] = ldg(oct.D[z] + (size_t)yc * pitch + xc);
+        for (int z = 0; z < ND; ++z) raw[rs][z] = ldg(oct.D[z] + off);
     };
     auto absorb = [&](int slot, int rs) {
 #pragma unroll
@@ -152,14 +152,22 @@ k_extrema(const OctaveDesc oct, int octave, float thr, Cand* __restrict__ cands,
                 vmin[z] = fmin3(hmin[z][0], hmin[z][1], hmin[z][2]);
                 vmax[z] = fmax3(hmax[z][0], hmax[z][1], hmax[z][2]);
             }
+            bool hit[ND - 2];
+            bool any = false;
 #pragma unroll
             for (int z = 1; z <= ND - 2; ++z) {
                 const float cv = ctr[z - 1][mid];
                 const float mx = fmax3(vmax[z - 1], vmax[z], vmax[z + 1]);
                 const float mn = fmin3(vmin[z - 1], vmin[z], vmin[z + 1]);
-                const bool hit = lane_out && fabsf(cv) > thr && (cv == mx || cv == mn);
-                const unsigned m = __ballot_sync(FULL, hit);
-                if (m) extrema_emit(m, hit, lane, x, y, z, octave, cands, cap, counters);
+                hit[z - 1] = lane_out && fabsf(cv) > thr && (cv == mx || cv == mn);
+                any |= hit[z - 1];
+            }
+            if (__ballot_sync(FULL, any)) {   // one vote per row; ~5 % of the rows hold an extremum
+#pragma unroll
+                for (int z = 1; z <= ND - 2; ++z) {
+                    const unsigned m = __ballot_sync(FULL, hit[z - 1]);
+                    if (m) extrema_emit(m, hit[z - 1], lane, x, y, z, octave, cands, cap, counters);
+                }
             }
         }
     }
