@@ -5,7 +5,7 @@
 // decimation image.cpp:41-55), bit-identical results, different data movement:
 //
 //   * a CTA owns a column strip of WS outputs and a band of rows and walks DOWN the rows, K rows per step;
-//     there is no y halo to recompute (only a pipeline fill of sum(R) rows per CTA) and no 2-D tile passing
+//     there is no y halo to recompute (only a pipeline fill of 2 sum(R) rows per CTA) and no 2-D tile passing
 //     through shared memory in barrier-separated passes;
 //   * the levels of the cascade form a pipeline over shared-memory row rings: the warps of level l read
 //     the rows that level l-1 completed in the previous step, so one CTA barrier per step is enough;
