@@ -46,6 +46,7 @@ def simulate(h, y0, y1, radii, K, PF):
     done = [[] for _ in range(NL + 1)]          # rows completed per level, in order
     next_fetch = sc["r0"]
     reads_this_step = []
+    reads_prev_step = []   # cp.async of step t is issued BEFORE barrier t: warps may still be reading step t-1's rows
 
     def fetch_rows(step_ready):
         nonlocal next_fetch
@@ -58,8 +59,10 @@ def simulate(h, y0, y1, radii, K, PF):
         slot = row % depth[l]
         old = ring[l].get(slot)
         if old is not None:
-            # the row being overwritten must not be read in this step or later
-            assert all(not (ll == l and rr == old[0]) for ll, rr in reads_this_step), (l, row, old)
+            # the row being overwritten must not be read in this step or later (for fetched rows: nor in the
+            # previous step, whose readers are not separated from this cp.async by a barrier)
+            live = reads_this_step + (reads_prev_step if l == 0 else [])
+            assert all(not (ll == l and rr == old[0]) for ll, rr in live), (l, row, old)
         ring[l][slot] = (row, step_ready)
 
     def read(l, row, t):
@@ -74,6 +77,7 @@ def simulate(h, y0, y1, radii, K, PF):
         fetch_rows(step_ready=g)
     state = {l: dict(i=sc["i0"][l]) for l in range(1, NL + 1)}
     for t in range(sc["steps"]):
+        reads_prev_step[:] = reads_this_step
         reads_this_step.clear()
         fetch_rows(step_ready=t + PF)
         # all levels run concurrently between two barriers: collect reads first, then writes
