@@ -452,6 +452,10 @@ int sift_b200_create(int device, int max_width, int max_height, sift_b200_ctx** 
     if (!out) return fail(nullptr, SIFT_B200_E_INVALID, "out is null");
     *out = nullptr;
     if (max_width < 2 || max_height < 2) return fail(nullptr, SIFT_B200_E_INVALID, "bad maximum image size");
+    // plane offsets are 32-bit in the scale-space kernels: the doubled base plane (pitch padded to 32) must hold
+    // fewer than 2^31 pixels (that is 32 768 x 16 384 input pixels; its arena would be ~100 GB anyway)
+    if ((2ll * max_width + 32) * (2ll * max_height) >= (1ll << 31))
+        return fail(nullptr, SIFT_B200_E_UNSUPPORTED, "maximum image size %d x %d is too large", max_width, max_height);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();

@@ -47,6 +47,17 @@ def test_no_device_is_a_loud_error_not_a_fallback(lib):
     assert e.value.code == 2 and "no CPU path" in str(e.value)
 
 
+def test_oversized_context_is_rejected_before_touching_a_device(lib):
+    """Plane offsets are 32-bit inside the scale-space kernels: a context whose doubled base plane would reach
+    2^31 pixels is refused with E_UNSUPPORTED (argument validation runs before the device query)."""
+    with pytest.raises(S.SiftError) as e:
+        S.SiftContext(40000, 40000)
+    assert e.value.code == 5 and "too large" in str(e.value)
+    with pytest.raises(S.SiftError) as e:
+        S.SiftContext(1, 64)
+    assert e.value.code != 0
+
+
 def test_product_never_references_the_oracle():
     """oracle/ is test infrastructure: nothing under sift_project_b200/ or include/ may name it."""
     bad = []
