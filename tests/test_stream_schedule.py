@@ -140,3 +140,20 @@ def test_schedule_matches_the_documented_start_rule():
         first_needed = max(sc["i0"][l + 1], 0)
         step_completed = sc["T"][l] + (first_needed + sc["R"][l] - sc["i0"][l])
         assert sc["T"][l + 1] == step_completed + 1
+
+
+def test_random_bands_property():
+    """Property test (hypothesis): any image height, any band inside it, any of the shipped / tested geometries."""
+    hypothesis = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(1, 700), st.data())
+    def run(h, data):
+        y0 = data.draw(st.integers(0, h - 1))
+        y1 = data.draw(st.integers(y0 + 1, h))
+        radii, K, PF = data.draw(st.sampled_from(GEOMS))
+        sc = simulate(h, y0, y1, radii, K, PF)
+        assert sc["steps"] >= -(-(y1 - y0) // K)
+
+    run()
