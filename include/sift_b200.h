@@ -11,7 +11,19 @@
  * reference's main.cpp relinks unchanged -- see INTEGRATION.md.
  *
  * Conventions: plain pointers and sizes, no C++/torch types; every call returns a status code
- * and never throws; sift_b200_last_error() gives the text.  All compute runs in hand-written
+ * and never throws; sift_b200_last_error() gives the text.
+ *
+ * Parity with the reference is NEAR-exact, not bit-exact: the reference computes in FP64 (image_io.hh:26 stores
+ * pixels as double), this build keeps the scale space in FP32 (an HBM-bound stage) and uses FP64 for every
+ * per-keypoint scalar.  What the tests enforce (tests/test_gpu_parity.py): keypoint recall / precision >= 99.5 % at
+ * 0.01 px / 1e-3 relative size; the descriptor STAGE within 1 quantisation level of the reference's on identical
+ * keypoints; end-to-end descriptor differences above 1 level only where the keypoint's own orientation / offset
+ * differs within those tolerances (attributed case by case); matcher output identical (integer-exact kernels).
+ *
+ * Streams: every context enqueues on its own non-blocking CUDA stream (sift_b200_stream()).  DEVICE pointers handed
+ * to a call are read / written in that stream's order: the caller must make the stream wait for whatever produced
+ * them (cudaStreamWaitEvent on sift_b200_stream(), or a synchronisation) and must not touch outputs before
+ * sift_b200_sync() / the stream's completion.  All compute runs in hand-written
  * sm_100a CUDA kernels; there is NO CPU fallback: without a usable CUDA device
  * sift_b200_create() fails with SIFT_B200_E_NO_DEVICE.
  */
@@ -87,7 +99,7 @@ const char* sift_b200_last_error(const sift_b200_ctx* ctx); /* ctx may be NULL: 
 
 /* detect_keypoints_and_descriptors (sift.cpp:712-776).
  * pixels: row-major, interleaved, channels = 1 (gray) or 3 (RGB), values 0..255; HOST or DEVICE
- * memory (detected).  The u8 entry point is exact for file-loaded images (image_io.cpp:27-33);
+ * memory (detected).  The u8 entry point loses nothing on the way in for file-loaded images (image_io.cpp:27-33);
  * the f32 one accepts arbitrary finite values of any range (its min / max are reduced on the GPU to
  * scale the fixed-point histograms; note that contrast_threshold assumes a 0..255 scale, sift.cpp:305).  out: HOST array of `capacity` records, filled in the
  * reference's order (sorted by Keypoint::operator<, sift.hh:31-41, duplicates removed).
@@ -153,6 +165,24 @@ int sift_b200_debug_extrema(sift_b200_ctx* ctx, int32_t* host_out, int capacity,
 /* stage 0 = raw (after refine, doubled-image frame), 1 = oriented (before sort/dedup) */
 int sift_b200_debug_keypoints(sift_b200_ctx* ctx, int stage, sift_b200_keypoint* host_out,
                               int capacity, int* count);
+/* Single stages on CALLER-SUPPLIED keypoints (HOST arrays) over the scale space of the last detect call, so that a
+ * parity test can attribute a difference to the stage that produced it.  debug_orient: compute_orientations
+ * (sift.cpp:447-533) on raw keypoints in the frame debug_keypoints(stage 0) returns them in; one output per
+ * histogram peak, unordered.  debug_describe: compute_descriptors (sift.cpp:610-682) on oriented keypoints (output
+ * frame), in place.  Both overwrite the lists of the last detect (its records can no longer be fetched). */
+int sift_b200_debug_orient(sift_b200_ctx* ctx, const sift_b200_keypoint* raw_in, int n, sift_b200_keypoint* out,
+                           int capacity, int* count);
+int sift_b200_debug_describe(sift_b200_ctx* ctx, sift_b200_keypoint* inout, int n);
+/* Launch plan switches (each: 0 / 1, or -1 to leave unchanged).  use_graph (default 1; env SIFT_B200_GRAPH): the
+ * stages after the input kernel are captured once per (image size, parameters) into a CUDA graph -- octave chain on
+ * one branch, second cascade kernel + extrema of each octave on another -- and replayed with one launch per image;
+ * 0 = plain launches on one stream.  centred (default 1; env SIFT_B200_CENTER): the scale space is stored relative
+ * to the input's mid level (u8: 128; float: the midpoint of its range), which makes the FP32 rounding steps 2-4x
+ * finer; every consumer takes differences, so results change only by less rounding.  extrema_form (default 0;
+ * env SIFT_B200_EXTREMA): 0 = the four-columns-per-lane extrema kernel, 1 = the one-column form (same set). */
+int sift_b200_debug_launch_plan(sift_b200_ctx* ctx, int use_graph, int centred, int extrema_form);
+/* how many CUDA graphs this context has captured so far (one per distinct image size / parameter set in a row) */
+long sift_b200_graphs_built(const sift_b200_ctx* ctx);
 /* number of kernel launches issued by this context since creation (bench's gpu_launches) */
 long sift_b200_launch_count(const sift_b200_ctx* ctx);
 

@@ -78,6 +78,8 @@ class _Lib:
         f("run_dog", C.POINTER(C.c_double), [C.c_void_p, C.c_int, C.c_int])
         f("run_extrema", C.c_int, [C.c_void_p, C.c_void_p, C.c_int])
         f("run_keypoints", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int])
+        f("run_orient_given", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int])
+        f("run_describe_given", C.c_int, [C.c_void_p, C.c_void_p, C.c_int])
 
     def _f(self, name, res, args):
         fn = getattr(self.lib, f"{self.p}_{name}")
@@ -152,6 +154,26 @@ class Run:
         n = self._l.run_keypoints(self._h, stage, None, 0)
         out = np.zeros(n, dtype=KP_DTYPE)
         self._l.run_keypoints(self._h, stage, out.ctypes.data, n)
+        return out
+
+    def orient_given(self, raw):
+        """compute_orientations (sift.cpp:447-533) on caller-supplied raw keypoints (doubled-image frame, as
+        stage 0 returns them) over this run's pyramid."""
+        raw = np.ascontiguousarray(raw, dtype=KP_DTYPE)
+        cap = 4 * len(raw) + 16
+        out = np.zeros(cap, dtype=KP_DTYPE)
+        n = self._l.run_orient_given(self._h, raw.ctypes.data, len(raw), out.ctypes.data, cap)
+        if n < 0:
+            raise RuntimeError("run was created without keep_pyramid")
+        return out[:n].copy()
+
+    def describe_given(self, kps):
+        """compute_descriptors (sift.cpp:610-682) on caller-supplied oriented keypoints; returns a copy with
+        .desc filled."""
+        out = np.ascontiguousarray(kps, dtype=KP_DTYPE).copy()
+        n = self._l.run_describe_given(self._h, out.ctypes.data, len(out))
+        if n < 0:
+            raise RuntimeError("run was created without keep_pyramid")
         return out
 
 

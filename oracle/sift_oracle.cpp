@@ -477,6 +477,34 @@ int oracle_run_extrema(const OracleRun* r, double* out, int cap) {
     return n;
 }
 
+// Stage functions on CALLER-SUPPLIED keypoints over this run's pyramid (needs keep_pyramid): used by the parity
+// tests to attribute a descriptor / orientation difference to the stage that produced it.
+// compute_orientations (sift.cpp:447-533) on `n` raw keypoints; returns the number of oriented keypoints.
+int oracle_run_orient_given(OracleRun* r, const OracleKeypoint* in, int n, OracleKeypoint* out, int cap) {
+    if (r->G.empty()) return -1;
+    std::vector<OracleKeypoint> raw(in, in + n), ori;
+    raw.swap(r->raw);
+    ori.swap(r->oriented);
+    orient(*r, r->p.double_image_size != 0);
+    const int m = (int)r->oriented.size();
+    if (out != nullptr)
+        for (int i = 0; i < m && i < cap; ++i) out[i] = r->oriented[i];
+    raw.swap(r->raw);
+    ori.swap(r->oriented);
+    return m;
+}
+
+// compute_descriptors (sift.cpp:610-682) on `n` oriented keypoints, in place (fills .desc).
+int oracle_run_describe_given(OracleRun* r, OracleKeypoint* inout, int n) {
+    if (r->G.empty()) return -1;
+    std::vector<OracleKeypoint> kps(inout, inout + n);
+    kps.swap(r->final_kps);
+    describe(*r, r->p.double_image_size != 0);
+    for (int i = 0; i < n; ++i) inout[i] = r->final_kps[i];
+    kps.swap(r->final_kps);
+    return n;
+}
+
 int oracle_run_keypoints(const OracleRun* r, int stage, OracleKeypoint* out, int cap) {
     const std::vector<OracleKeypoint>& v = stage == 0 ? r->raw : stage == 1 ? r->oriented : r->final_kps;
     int n = (int)v.size();

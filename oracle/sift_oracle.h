@@ -56,6 +56,12 @@ int oracle_run_extrema(const OracleRun* r, double* out_xyzo, int cap);
 /* stage 0 = raw (after refine), 1 = oriented, 2 = final (sorted, deduplicated, described) */
 int oracle_run_keypoints(const OracleRun* r, int stage, OracleKeypoint* out, int cap);
 
+/* The per-keypoint stages on caller-supplied keypoints over this run's pyramid (keep_pyramid must be on):
+ * compute_orientations (sift.cpp:447-533) on raw keypoints, compute_descriptors (sift.cpp:610-682) on
+ * oriented keypoints (in place).  Return the output count, -1 without a pyramid. */
+int oracle_run_orient_given(OracleRun* r, const OracleKeypoint* in, int n, OracleKeypoint* out, int cap);
+int oracle_run_describe_given(OracleRun* r, OracleKeypoint* inout, int n);
+
 /* match_keypoints (sift.cpp:783-815) on raw 128-byte descriptors; returns the match count. */
 int oracle_match(const uint8_t* desc_a, int na, const uint8_t* desc_b, int nb, double ratio,
                  int* idx_a, int* idx_b, double* dist, int cap);

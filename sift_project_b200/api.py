@@ -97,6 +97,10 @@ def load_library():
         "sift_b200_debug_extrema": (i32, [vp, vp, i32, i32p]),
         "sift_b200_debug_keypoints": (i32, [vp, i32, vp, i32, i32p]),
         "sift_b200_launch_count": (C.c_long, [vp]),
+        "sift_b200_graphs_built": (C.c_long, [vp]),
+        "sift_b200_debug_orient": (i32, [vp, vp, i32, vp, i32, i32p]),
+        "sift_b200_debug_describe": (i32, [vp, vp, i32]),
+        "sift_b200_debug_launch_plan": (i32, [vp, i32, i32, i32]),
         "sift_b200_result_copy": (i32, [vp, vp, i32, i32p]),
         "sift_b200_set_profiling": (i32, [vp, i32]),
         "sift_b200_get_profile": (i32, [vp, vp, vp]),
@@ -297,6 +301,30 @@ class SiftContext:
         out = np.zeros((max(n.value, 1), 4), np.int32)
         self._check(self._L.sift_b200_debug_extrema(self._h, out.ctypes.data, n.value, C.byref(n)))
         return out[: n.value]
+
+    def launch_plan(self, use_graph=None, centred=None, extrema_form=None):
+        self._check(self._L.sift_b200_debug_launch_plan(self._h, -1 if use_graph is None else int(use_graph),
+                                                        -1 if centred is None else int(centred),
+                                                        -1 if extrema_form is None else int(extrema_form)))
+
+    @property
+    def graphs_built(self):
+        return self._L.sift_b200_graphs_built(self._h)
+
+    def orient_given(self, raw):
+        """compute_orientations on caller-supplied raw keypoints over the last detect's scale space."""
+        raw = np.ascontiguousarray(raw, dtype=KP_DTYPE)
+        cap = 4 * len(raw) + 16
+        out = np.zeros(cap, dtype=KP_DTYPE)
+        n = C.c_int(0)
+        self._check(self._L.sift_b200_debug_orient(self._h, raw.ctypes.data, len(raw), out.ctypes.data, cap, C.byref(n)))
+        return out[: n.value].copy()
+
+    def describe_given(self, kps):
+        """compute_descriptors on caller-supplied oriented keypoints; returns a copy with .desc filled."""
+        out = np.ascontiguousarray(kps, dtype=KP_DTYPE).copy()
+        self._check(self._L.sift_b200_debug_describe(self._h, out.ctypes.data, len(out)))
+        return out
 
     def stage_keypoints(self, stage):
         n = C.c_int(0)

@@ -8,6 +8,8 @@
 //   -> clean_keypoints :20-24 -> compute_descriptors :610-682.
 #include <math.h>
 #include <stdarg.h>
+#include <stdint.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -59,6 +61,24 @@ struct sift_b200_ctx {
     bool keep_planes = false;    // also store G[4], G[5] (debug plane access)
     bool force_unfused = false;  // per-level kernels instead of the fused octave cascade
     int fused_mode = 0;          // launch_octave_fused mode: 0 auto, 2 tile kernels only, 3 streaming kernels only
+    bool centred = true;         // scale space stored relative to the input's mid level (finer FP32 steps, same results)
+    float centre_u8 = 128.f;
+    bool last_float_input = false;
+    bool pyramid_valid = false;  // the planes of the last detect are intact (debug stage calls need them)
+    // ---- launch plan: everything after the input stage is replayed from a CUDA graph; inside it the octave
+    // chain (first cascade kernel of every octave) runs on the main stream and the second cascade kernel + the
+    // extrema scan of each octave on a side stream, so the small octaves overlap the large ones ----
+    bool use_graph = true;
+    int extrema_form = 0;        // 0 = four columns per lane (default), 1 = one column per lane
+    cudaStream_t side = nullptr;
+    std::vector<cudaEvent_t> fork_ev;   // [0 .. kMaxOctaves): "octave chain reached o"; last: join
+    cudaGraphExec_t graph_exec = nullptr;
+    std::vector<uint8_t> graph_key;
+    int graph_launches = 0;
+    int graph_stage_launches[SIFT_B200_STAGE_COUNT] = {0};
+    long graphs_built = 0;
+    PyramidDesc pyr_uploaded;    // what d_pyr holds
+    bool pyr_uploaded_valid = false;
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_stage;   // stage of the interval ending at event i (event 0: -1)
@@ -173,7 +193,10 @@ int check_params(sift_b200_ctx* c, const sift_b200_params& p) {
 }
 
 int grow_i32(sift_b200_ctx* c, int** p, size_t n) {
-    if (*p) cudaFree(*p);
+    if (*p) {
+        CU(c, cudaStreamSynchronize(c->stream));   // earlier matcher launches may still read the old buffer
+        cudaFree(*p);
+    }
     *p = nullptr;
     CU(c, cudaMalloc(p, n * sizeof(int)));
     return SIFT_B200_OK;
@@ -227,6 +250,80 @@ void prof_mark(sift_b200_ctx* c, int stage, int launches = 0) {
     c->ev_used++;
 }
 
+// Everything of one detect call that follows the input stage: cascade + DoG + extrema per octave, refine,
+// orientation, sort / dedup, descriptors, counters back to the host.  `forked`: the first cascade kernel of every
+// octave (which also writes the next octave's base) stays on the main stream, the second cascade kernel and the
+// extrema scan of each octave go to the side stream, joined before the refinement -- the octave chain is the only
+// true dependency (sift.cpp:187-199), so the many small launches of the low octaves overlap the large ones.
+// Enqueued either directly (profiling, debugging) or once under stream capture and replayed as a CUDA graph.
+struct DetectPlan {
+    int octaves, layers, dogs;
+    bool fused;
+    BlurTaps taps[kMaxLayers];
+};
+
+int enqueue_body(sift_b200_ctx* c, const DetectPlan& pl, bool forked, int* n_launches, int* stage_launches) {
+    const StageParams& sp = c->sp;
+    cudaStream_t s = c->stream, s2 = forked ? c->side : c->stream;
+    int total = 0;
+    auto mark = [&](int stage, int launches) {
+        total += launches;
+        if (stage_launches) stage_launches[stage] += launches;
+        if (!forked) prof_mark(c, stage, 0);
+    };
+    for (int o = 0; o < pl.octaves; ++o) {
+        OctaveDesc& od = c->pyr.oct[o];
+        float* dec = nullptr;
+        int dw = 0, dh = 0, dp = 0;
+        if (o + 1 < pl.octaves) {  // next base = G[layers-3] decimated, sift.cpp:195-196
+            OctaveDesc& nx = c->pyr.oct[o + 1];
+            dec = nx.G[0]; dw = nx.w; dh = nx.h; dp = nx.pitch;
+        }
+        if (pl.fused) {
+            CU(c, launch_octave_fused(od, pl.taps, dec, dw, dh, dp, c->keep_planes, c->sm_count, c->fused_mode, 1, s));
+            if (forked) {
+                CU(c, cudaEventRecord(c->fork_ev[o], s));
+                CU(c, cudaStreamWaitEvent(s2, c->fork_ev[o], 0));
+            }
+            if (o == 0) mark(SIFT_B200_STAGE_PYRAMID, 1);   // the two largest launches are timed one by one
+            CU(c, launch_octave_fused(od, pl.taps, dec, dw, dh, dp, c->keep_planes, c->sm_count, c->fused_mode, 2, s2));
+            mark(SIFT_B200_STAGE_PYRAMID, o == 0 ? 1 : 2);
+        } else {
+            for (int i = 1; i < pl.layers; ++i) {
+                const bool last = i == pl.layers - 3;
+                CU(c, launch_blur(od.G[i - 1], od.G[i], od.D[i - 1], last ? dec : nullptr, od.w, od.h, od.pitch,
+                                  last ? dw : 0, last ? dh : 0, last ? dp : 0, pl.taps[i], s));
+            }
+            if (forked) {
+                CU(c, cudaEventRecord(c->fork_ev[o], s));
+                CU(c, cudaStreamWaitEvent(s2, c->fork_ev[o], 0));
+            }
+            mark(SIFT_B200_STAGE_PYRAMID, pl.layers - 1);
+        }
+        if (od.w >= 2 * sp.border + 1 && od.h >= 2 * sp.border + 1) {
+            CU(c, launch_extrema(od, o, pl.dogs, sp.border, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, c->extrema_form, s2));
+            mark(SIFT_B200_STAGE_EXTREMA, 1);
+        }
+    }
+    if (forked) {
+        CU(c, cudaEventRecord(c->fork_ev[kMaxOctaves], s2));
+        CU(c, cudaStreamWaitEvent(s, c->fork_ev[kMaxOctaves], 0));
+    }
+    CU(c, launch_refine(c->d_pyr, c->d_cands, c->d_raw, c->d_counters, sp, c->sm_count, s));
+    mark(SIFT_B200_STAGE_REFINE, 1);
+    CU(c, launch_orient(c->d_pyr, c->d_raw, c->d_oriented, c->d_counters, sp, c->sm_count, s));
+    mark(SIFT_B200_STAGE_ORIENT, 1);
+    int l = 0;
+    CU(c, launch_sort_dedup(c->d_oriented, c->d_counters, c->ss, sp, c->sm_count, s, &l));
+    mark(SIFT_B200_STAGE_SORT, l);
+    CU(c, launch_describe(c->d_pyr, c->d_oriented, c->ss.final_order, c->d_counters, c->d_records, c->d_desc,
+                          c->cap_oriented, sp, c->sm_count, s));
+    mark(SIFT_B200_STAGE_DESCRIBE, 1);
+    CU(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    if (n_launches) *n_launches = total;
+    return SIFT_B200_OK;
+}
+
 template <typename T>
 int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, int channels,
                    const sift_b200_params& p) {
@@ -234,13 +331,14 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     if (rc) return rc;
     if (width < 2 || height < 2) return fail(c, SIFT_B200_E_INVALID, "image %dx%d is too small", width, height);
     if (channels != 1 && channels != 3) return fail(c, SIFT_B200_E_INVALID, "channels must be 1 or 3");
-    if (width + 2 > c->ss_nb_cap)
+    if (width > c->max_w || height > c->max_h)
         return fail(c, SIFT_B200_E_TOO_LARGE, "image %dx%d exceeds the context's %dx%d", width, height,
                     c->max_w, c->max_h);
     const int doubled = p.double_image_size ? 1 : 0;
     const int bw = doubled ? 2 * width : width, bh = doubled ? 2 * height : height;
     const int layers = p.intervals + 3, dogs = p.intervals + 2;
-    if (arena_need(bw, bh, layers + dogs) > c->arena_floats)
+    // 32-bit plane offsets in the scale-space kernels (also checked for the context's maximum at creation)
+    if ((long long)round_up(bw, 32) * bh >= (1ll << 31) || arena_need(bw, bh, layers + dogs) > c->arena_floats)
         return fail(c, SIFT_B200_E_TOO_LARGE, "image %dx%d exceeds the context's workspace", width, height);
     int octaves = octave_count(bw, bh);
     if (p.max_octaves > 0) octaves = std::min(octaves, p.max_octaves);
@@ -251,10 +349,16 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     c->layers = layers; c->dogs = dogs;
     c->base_w = bw; c->base_h = bh;
     cudaStream_t s = c->stream;
-    CU(c, cudaMemcpyAsync(c->d_pyr, &c->pyr, sizeof(PyramidDesc), cudaMemcpyHostToDevice, s));
+    if (!c->pyr_uploaded_valid || memcmp(&c->pyr, &c->pyr_uploaded, sizeof(PyramidDesc)) != 0) {
+        // pageable source: the copy is staged before the call returns, so c->pyr may change afterwards
+        CU(c, cudaMemcpyAsync(c->d_pyr, &c->pyr, sizeof(PyramidDesc), cudaMemcpyHostToDevice, s));
+        memcpy(&c->pyr_uploaded, &c->pyr, sizeof(PyramidDesc));
+        c->pyr_uploaded_valid = true;
+    }
     CU(c, cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), s));
 
     StageParams& sp = c->sp;
+    memset(&sp, 0, sizeof sp);   // (it is part of the graph key: no indeterminate padding)
     sp.doubled = doubled;
     sp.intervals = p.intervals;
     sp.dogs = dogs;
@@ -262,8 +366,9 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     sp.border = p.window_size / 2;
     sp.mag_bound = 361.0;   // > sqrt(2) * 255
     sp.range = nullptr;
+    c->last_float_input = sizeof(T) != 1;
     if (sizeof(T) != 1) {   // float input: any range -- reduce it on the device
-        CU(c, launch_range((const float*)d_pixels, (size_t)width * height * channels, c->d_range, s));
+        CU(c, launch_range((const float*)d_pixels, (size_t)width * height * channels, c->d_range, c->sm_count, s));
         sp.range = c->d_range;
         c->launches += 1;
     }
@@ -283,6 +388,7 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     c->stats.base_width = bw;
     c->stats.base_height = bh;
     c->have_result = false;
+    c->pyramid_valid = false;
     c->ev_used = 0;
     memset(c->stage_launches, 0, sizeof c->stage_launches);
     prof_mark(c, -1);
@@ -293,11 +399,14 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     }
 
     // Scale-space sigmas, compute_gaussian_kernels sift.cpp:143-155.
+    DetectPlan pl;
+    memset(&pl, 0, sizeof pl);
+    pl.octaves = octaves; pl.layers = layers; pl.dogs = dogs;
     double sig[kMaxLayers];
     const double k = pow(2.0, 1.0 / p.intervals);
     sig[0] = p.init_sigma;
     for (int i = 1; i < layers; ++i) sig[i] = pow(k, i - 1) * p.init_sigma * sqrt(k * k - 1);
-    BlurTaps taps[kMaxLayers];
+    BlurTaps* taps = pl.taps;
     taps[0] = make_taps(sqrt(p.init_sigma * p.init_sigma - 1.0));  // sift.cpp:124: "-1" in both modes
     for (int i = 1; i < layers; ++i) taps[i] = make_taps(sig[i]);
     for (int i = 0; i < layers; ++i)
@@ -305,68 +414,65 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
             return fail(c, SIFT_B200_E_UNSUPPORTED, "blur radius %d > %d (init_sigma / intervals combination)",
                         taps[i].radius, kMaxRadius);
 
-    // Stage 0: gray (+2x) into a scratch plane (octave 0's G[5] slot, dead until the cascade
-    // reaches it), then the initial blur into G[0].
+    // Stage 0: gray (+2x) into a scratch plane (octave 0's last G slot, dead until the cascade
+    // reaches it), then the initial blur into G[0].  Not part of the graph: the input pointer changes per call.
     OctaveDesc& o0 = c->pyr.oct[0];
     float* scratch = o0.G[layers - 1];
+    const float centre = c->centred ? c->centre_u8 : 0.f;
     if (sizeof(T) == 1 && input_fused_supported(channels, taps[0]) && !c->force_unfused) {
-        CU(c, launch_input_u8((const uint8_t*)d_pixels, width, height, o0.G[0], bw, bh, o0.pitch, doubled, taps[0], s));
+        CU(c, launch_input_u8((const uint8_t*)d_pixels, width, height, o0.G[0], bw, bh, o0.pitch, doubled, taps[0], centre, s));
         prof_mark(c, SIFT_B200_STAGE_INPUT, 1);
     } else {
-    if (sizeof(T) == 1)
-        CU(c, launch_prepare_u8((const uint8_t*)d_pixels, width, height, channels, scratch, bw, bh, o0.pitch,
-                                doubled, s));
-    else
-        CU(c, launch_prepare_f32((const float*)d_pixels, width, height, channels, scratch, bw, bh, o0.pitch,
-                                 doubled, s));
-    CU(c, launch_blur(scratch, o0.G[0], nullptr, nullptr, bw, bh, o0.pitch, 0, 0, 0, taps[0], s));
-    prof_mark(c, SIFT_B200_STAGE_INPUT, 2);
+        if (sizeof(T) == 1)
+            CU(c, launch_prepare_u8((const uint8_t*)d_pixels, width, height, channels, scratch, bw, bh, o0.pitch,
+                                    doubled, centre, s));
+        else
+            CU(c, launch_prepare_f32((const float*)d_pixels, width, height, channels, scratch, bw, bh, o0.pitch,
+                                     doubled, c->centred ? c->d_range : nullptr, s));
+        CU(c, launch_blur(scratch, o0.G[0], nullptr, nullptr, bw, bh, o0.pitch, 0, 0, 0, taps[0], s));
+        prof_mark(c, SIFT_B200_STAGE_INPUT, 2);
     }
 
-    const bool fused = p.intervals == 3 && cascade_supported(taps) && !c->force_unfused;
-    for (int o = 0; o < octaves; ++o) {
-        OctaveDesc& od = c->pyr.oct[o];
-        if (fused) {
-            float* dec = nullptr;
-            int dw = 0, dh = 0, dp = 0;
-            if (o + 1 < octaves) {  // next base = G[3] decimated, sift.cpp:195-196
-                OctaveDesc& nx = c->pyr.oct[o + 1];
-                dec = nx.G[0]; dw = nx.w; dh = nx.h; dp = nx.pitch;
-            }
-            CU(c, launch_octave_fused(od, taps, dec, dw, dh, dp, c->keep_planes, c->sm_count, c->fused_mode, 1, s));
-            if (o == 0) prof_mark(c, SIFT_B200_STAGE_PYRAMID, 1);   // the two largest launches are timed one by one
-            CU(c, launch_octave_fused(od, taps, dec, dw, dh, dp, c->keep_planes, c->sm_count, c->fused_mode, 2, s));
-            prof_mark(c, SIFT_B200_STAGE_PYRAMID, o == 0 ? 1 : 2);
-        } else {
-        for (int i = 1; i < layers; ++i) {
-            float* dec = nullptr;
-            int dw = 0, dh = 0, dp = 0;
-            if (i == layers - 3 && o + 1 < octaves) {  // next base = G[layers-3] decimated, sift.cpp:195-196
-                OctaveDesc& nx = c->pyr.oct[o + 1];
-                dec = nx.G[0]; dw = nx.w; dh = nx.h; dp = nx.pitch;
-            }
-            CU(c, launch_blur(od.G[i - 1], od.G[i], od.D[i - 1], dec, od.w, od.h, od.pitch, dw, dh, dp, taps[i], s));
-        }
-        prof_mark(c, SIFT_B200_STAGE_PYRAMID, layers - 1);
-        }
-        if (od.w >= 2 * sp.border + 1 && od.h >= 2 * sp.border + 1) {
-            CU(c, launch_extrema(od, o, dogs, sp.border, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, s));
-            prof_mark(c, SIFT_B200_STAGE_EXTREMA, 1);
-        }
-    }
-    CU(c, launch_refine(c->d_pyr, c->d_cands, c->d_raw, c->d_counters, sp, s));
-    prof_mark(c, SIFT_B200_STAGE_REFINE, 1);
-    CU(c, launch_orient(c->d_pyr, c->d_raw, c->d_oriented, c->d_counters, sp, s));
-    prof_mark(c, SIFT_B200_STAGE_ORIENT, 1);
+    pl.fused = p.intervals == 3 && cascade_supported(taps) && !c->force_unfused;
     c->ss.nb = std::min(width + 2, c->ss_nb_cap);
-    int l = 0;
-    CU(c, launch_sort_dedup(c->d_oriented, c->d_counters, c->ss, sp, s, &l));
-    prof_mark(c, SIFT_B200_STAGE_SORT, l);
-    CU(c, launch_describe(c->d_pyr, c->d_oriented, c->ss.final_order, c->d_counters, c->d_records, c->d_desc,
-                          c->cap_oriented, sp, s));
-    prof_mark(c, SIFT_B200_STAGE_DESCRIBE, 1);
-    CU(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
     c->detect_pending = true;
+    if (!c->use_graph || c->profiling) {
+        int n = 0;
+        rc = enqueue_body(c, pl, false, &n, c->stage_launches);
+        c->launches += n;
+        return rc;
+    }
+    // graph key: everything the captured launches depend on (geometry, taps, stage parameters, debug switches)
+    std::vector<uint8_t> key;
+    auto put = [&](const void* q, size_t n) { key.insert(key.end(), (const uint8_t*)q, (const uint8_t*)q + n); };
+    put(&pl, sizeof pl); put(&sp, sizeof sp); put(&c->pyr, sizeof c->pyr); put(&c->ss.nb, sizeof(int));
+    const int dbg[4] = {c->keep_planes, c->force_unfused, c->fused_mode, c->extrema_form};
+    put(dbg, sizeof dbg);
+    if (!c->graph_exec || key != c->graph_key) {
+        if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+        memset(c->graph_stage_launches, 0, sizeof c->graph_stage_launches);
+        CU(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_body(c, pl, true, &c->graph_launches, c->graph_stage_launches);
+        cudaGraph_t g = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(s, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); c->detect_pending = false; return rc; }
+        if (e != cudaSuccess) {
+            c->detect_pending = false;
+            return fail(c, SIFT_B200_E_CUDA, "stream capture failed: %s", cudaGetErrorString(e));
+        }
+        const cudaError_t e2 = cudaGraphInstantiate(&c->graph_exec, g, 0);
+        cudaGraphDestroy(g);
+        if (e2 != cudaSuccess) {
+            c->graph_exec = nullptr;
+            c->detect_pending = false;
+            return fail(c, SIFT_B200_E_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e2));
+        }
+        c->graph_key.swap(key);
+        c->graphs_built++;
+    }
+    CU(c, cudaGraphLaunch(c->graph_exec, s));
+    c->launches += c->graph_launches;
+    for (int i = 0; i < SIFT_B200_STAGE_COUNT; ++i) c->stage_launches[i] += c->graph_stage_launches[i];
     return SIFT_B200_OK;
 }
 
@@ -388,6 +494,7 @@ int finish_detect(sift_b200_ctx* c, int* count) {
                         k.n_extrema, c->cap_extrema, k.n_raw, c->cap_raw, k.n_oriented, c->cap_oriented);
         }
         c->have_result = true;
+        c->pyramid_valid = true;
     }
     if (count) *count = c->stats.final_keypoints;
     return SIFT_B200_OK;
@@ -477,6 +584,9 @@ int sift_b200_create(int device, int max_width, int max_height, sift_b200_ctx** 
         c->force_unfused = v == 1;
         c->fused_mode = v == 2 || v == 3 ? v : 0;
     }
+    if (const char* m = getenv("SIFT_B200_CENTER")) c->centred = atoi(m) != 0;   // experiments
+    if (const char* m = getenv("SIFT_B200_GRAPH")) c->use_graph = atoi(m) != 0;
+    if (const char* m = getenv("SIFT_B200_EXTREMA")) c->extrema_form = atoi(m) == 1 ? 1 : 0;
     c->max_w = max_width;
     c->max_h = max_height;
 #define CRT(call)                                                                                   \
@@ -490,6 +600,12 @@ int sift_b200_create(int device, int max_width, int max_height, sift_b200_ctx** 
     } while (0)
     CRT(cudaSetDevice(device));
     CRT(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CRT(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    for (int i = 0; i <= kMaxOctaves; ++i) {
+        cudaEvent_t e;
+        CRT(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->fork_ev.push_back(e);
+    }
     CRT(pyramid_init());
     CRT(match_init());
     c->arena_floats = arena_need(2 * max_width, 2 * max_height, kMaxLayers + kMaxDogs);
@@ -539,7 +655,10 @@ void sift_b200_destroy(sift_b200_ctx* c) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->fork_ev) cudaEventDestroy(e);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->side) cudaStreamDestroy(c->side);
     if (c->stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
     delete c;
@@ -664,6 +783,8 @@ int sift_b200_match_enqueue(sift_b200_ctx* c, const uint8_t* d_a, int na, const 
     if (!c) return SIFT_B200_E_INVALID;
     if (na < 0 || nb < 0 || (na > 0 && (!d_a || !d_best_idx || !d_best_d2 || !d_second_d2)) || (nb > 0 && !d_b))
         return fail(c, SIFT_B200_E_INVALID, "bad match arguments");
+    if (((uintptr_t)d_a | (uintptr_t)d_b) & 15)
+        return fail(c, SIFT_B200_E_INVALID, "descriptor matrices must be 16-byte aligned");
     CU(c, cudaSetDevice(c->device));
     if (na == 0) return SIFT_B200_OK;
     return enqueue_match(c, d_a, na, d_b, nb, d_best_idx, d_best_d2, d_second_d2);
@@ -681,8 +802,12 @@ int sift_b200_match(sift_b200_ctx* c, const uint8_t* desc_a, int na, const uint8
     cudaStream_t s = c->stream;
     const uint8_t* d_a = desc_a;
     const uint8_t* d_b = desc_b;
-    if (!is_device_ptr(desc_a)) {
+    const bool dev_a = is_device_ptr(desc_a), dev_b = is_device_ptr(desc_b);
+    if ((dev_a && ((uintptr_t)desc_a & 15)) || (dev_b && ((uintptr_t)desc_b & 15)))
+        return fail(c, SIFT_B200_E_INVALID, "device descriptor matrices must be 16-byte aligned");
+    if (!dev_a) {
         if ((size_t)na > c->ma_cap) {
+            CU(c, cudaStreamSynchronize(s));
             if (c->d_ma) cudaFree(c->d_ma);
             c->d_ma = nullptr;
             c->ma_cap = (size_t)na * 5 / 4 + 1024;
@@ -691,8 +816,9 @@ int sift_b200_match(sift_b200_ctx* c, const uint8_t* desc_a, int na, const uint8
         CU(c, cudaMemcpyAsync(c->d_ma, desc_a, (size_t)na * 128, cudaMemcpyHostToDevice, s));
         d_a = c->d_ma;
     }
-    if (!is_device_ptr(desc_b)) {
+    if (!dev_b) {
         if ((size_t)nb > c->mb_cap) {
+            CU(c, cudaStreamSynchronize(s));
             if (c->d_mb) cudaFree(c->d_mb);
             c->d_mb = nullptr;
             c->mb_cap = (size_t)nb * 5 / 4 + 1024;
@@ -709,7 +835,10 @@ int sift_b200_match(sift_b200_ctx* c, const uint8_t* desc_a, int na, const uint8
         if ((rc = grow_i32(c, &c->d_second_d2, rows))) return rc;
         if ((rc = grow_i32(c, &c->d_out_ia, rows))) return rc;
         if ((rc = grow_i32(c, &c->d_out_ib, rows))) return rc;
-        if (c->d_out_dist) cudaFree(c->d_out_dist);
+        if (c->d_out_dist) {
+            CU(c, cudaStreamSynchronize(s));
+            cudaFree(c->d_out_dist);
+        }
         c->d_out_dist = nullptr;
         CU(c, cudaMalloc(&c->d_out_dist, rows * sizeof(double)));
         c->best_cap = rows;
@@ -725,9 +854,10 @@ int sift_b200_match(sift_b200_ctx* c, const uint8_t* desc_a, int na, const uint8
     *count = n;
     const int ncopy = std::min(n, capacity);
     if (ncopy > 0) {
-        CU(c, cudaMemcpy(idx_a, c->d_out_ia, (size_t)ncopy * sizeof(int), cudaMemcpyDeviceToHost));
-        CU(c, cudaMemcpy(idx_b, c->d_out_ib, (size_t)ncopy * sizeof(int), cudaMemcpyDeviceToHost));
-        CU(c, cudaMemcpy(dist, c->d_out_dist, (size_t)ncopy * sizeof(double), cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpyAsync(idx_a, c->d_out_ia, (size_t)ncopy * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU(c, cudaMemcpyAsync(idx_b, c->d_out_ib, (size_t)ncopy * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU(c, cudaMemcpyAsync(dist, c->d_out_dist, (size_t)ncopy * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU(c, cudaStreamSynchronize(s));
     }
     if (n > capacity) return fail(c, SIFT_B200_E_CAPACITY, "%d matches, output capacity %d", n, capacity);
     return SIFT_B200_OK;
@@ -770,6 +900,15 @@ int sift_b200_debug_plane(sift_b200_ctx* c, int kind, int octave, int layer, flo
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaMemcpy2D(host_out, (size_t)od.w * sizeof(float), src, (size_t)od.pitch * sizeof(float),
                        (size_t)od.w * sizeof(float), od.h, cudaMemcpyDeviceToHost));
+    if (kind == SIFT_B200_PLANE_GAUSSIAN && c->centred) {   // the planes are stored relative to the input's mid level
+        float centre = c->centre_u8;
+        if (c->last_float_input) {
+            float r[2];
+            CU(c, cudaMemcpy(r, c->d_range, sizeof r, cudaMemcpyDeviceToHost));
+            centre = (float)(0.5 * ((double)r[0] + (double)r[1]));
+        }
+        for (size_t i = 0, n = (size_t)od.w * od.h; i < n; ++i) host_out[i] += centre;
+    }
     return SIFT_B200_OK;
 }
 
@@ -805,6 +944,101 @@ int sift_b200_debug_keypoints(sift_b200_ctx* c, int stage, sift_b200_keypoint* h
     }
     return SIFT_B200_OK;
 }
+
+// ---- single stages on caller-supplied keypoints over the last detect's scale space (parity attribution) ----
+static int debug_stage_ready(sift_b200_ctx* c) {
+    if (c->detect_pending) {
+        int rc = finish_detect(c, nullptr);
+        if (rc) return rc;
+    }
+    if (!c->pyramid_valid || c->stats.octaves == 0)
+        return fail(c, SIFT_B200_E_INVALID, "no scale space: run a detect call first");
+    return SIFT_B200_OK;
+}
+
+int sift_b200_debug_orient(sift_b200_ctx* c, const sift_b200_keypoint* raw_in, int n, sift_b200_keypoint* out,
+                           int capacity, int* count) {
+    if (!c || !count || n < 0 || (n > 0 && !raw_in) || (capacity > 0 && !out)) return SIFT_B200_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    int rc = debug_stage_ready(c);
+    if (rc) return rc;
+    if (n > c->cap_raw) return fail(c, SIFT_B200_E_CAPACITY, "%d keypoints, capacity %d", n, c->cap_raw);
+    for (int i = 0; i < n; ++i)
+        if (raw_in[i].octave < 0 || raw_in[i].octave >= c->stats.octaves || raw_in[i].layer < 1 ||
+            raw_in[i].layer > c->layers - 3)
+            return fail(c, SIFT_B200_E_INVALID, "keypoint %d: octave / layer outside the scale space", i);
+    std::vector<KpCore> tmp(std::max(n, 1));
+    for (int i = 0; i < n; ++i)
+        tmp[i] = KpCore{raw_in[i].x, raw_in[i].y, raw_in[i].octave, raw_in[i].layer, raw_in[i].size, raw_in[i].pori};
+    Counters k;
+    memset(&k, 0, sizeof k);
+    k.n_raw = n;
+    cudaStream_t s = c->stream;
+    c->have_result = false;   // the lists of the detect call are overwritten
+    CU(c, cudaMemcpyAsync(c->d_raw, tmp.data(), (size_t)n * sizeof(KpCore), cudaMemcpyHostToDevice, s));
+    CU(c, cudaMemcpyAsync(c->d_counters, &k, sizeof k, cudaMemcpyHostToDevice, s));
+    CU(c, launch_orient(c->d_pyr, c->d_raw, c->d_oriented, c->d_counters, c->sp, c->sm_count, s));
+    CU(c, cudaMemcpyAsync(&k, c->d_counters, sizeof k, cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));
+    c->launches += 1;
+    *count = k.n_oriented;
+    if (k.n_oriented > c->cap_oriented) return fail(c, SIFT_B200_E_CAPACITY, "oriented list overflow");
+    const int ncopy = std::min(k.n_oriented, capacity);
+    if (ncopy > 0) {
+        tmp.resize(ncopy);
+        CU(c, cudaMemcpy(tmp.data(), c->d_oriented, (size_t)ncopy * sizeof(KpCore), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < ncopy; ++i) {
+            memset(&out[i], 0, sizeof(sift_b200_keypoint));
+            out[i].x = tmp[i].x; out[i].y = tmp[i].y; out[i].octave = tmp[i].octave; out[i].layer = tmp[i].layer;
+            out[i].size = tmp[i].size; out[i].pori = tmp[i].pori;
+        }
+    }
+    if (k.n_oriented > capacity) return fail(c, SIFT_B200_E_CAPACITY, "%d keypoints, output capacity %d", k.n_oriented, capacity);
+    return SIFT_B200_OK;
+}
+
+int sift_b200_debug_describe(sift_b200_ctx* c, sift_b200_keypoint* inout, int n) {
+    if (!c || n < 0 || (n > 0 && !inout)) return SIFT_B200_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    int rc = debug_stage_ready(c);
+    if (rc) return rc;
+    if (n > c->cap_oriented) return fail(c, SIFT_B200_E_CAPACITY, "%d keypoints, capacity %d", n, c->cap_oriented);
+    for (int i = 0; i < n; ++i)
+        if (inout[i].octave < 0 || inout[i].octave >= c->stats.octaves || inout[i].layer < 0 ||
+            inout[i].layer >= c->layers)
+            return fail(c, SIFT_B200_E_INVALID, "keypoint %d: octave / layer outside the scale space", i);
+    if (n == 0) return SIFT_B200_OK;
+    std::vector<KpCore> tmp(n);
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) {
+        tmp[i] = KpCore{inout[i].x, inout[i].y, inout[i].octave, inout[i].layer, inout[i].size, inout[i].pori};
+        order[i] = i;
+    }
+    Counters k;
+    memset(&k, 0, sizeof k);
+    k.n_final = n;
+    cudaStream_t s = c->stream;
+    c->have_result = false;
+    CU(c, cudaMemcpyAsync(c->d_oriented, tmp.data(), (size_t)n * sizeof(KpCore), cudaMemcpyHostToDevice, s));
+    CU(c, cudaMemcpyAsync(c->ss.final_order, order.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+    CU(c, cudaMemcpyAsync(c->d_counters, &k, sizeof k, cudaMemcpyHostToDevice, s));
+    CU(c, launch_describe(c->d_pyr, c->d_oriented, c->ss.final_order, c->d_counters, c->d_records, c->d_desc,
+                          c->cap_oriented, c->sp, c->sm_count, s));
+    CU(c, cudaMemcpyAsync(inout, c->d_records, (size_t)n * sizeof(sift_b200_keypoint), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));
+    c->launches += 1;
+    return SIFT_B200_OK;
+}
+
+int sift_b200_debug_launch_plan(sift_b200_ctx* c, int use_graph, int centred, int extrema_form) {
+    if (!c) return SIFT_B200_E_INVALID;
+    if (use_graph >= 0) c->use_graph = use_graph != 0;
+    if (centred >= 0) c->centred = centred != 0;
+    if (extrema_form >= 0) c->extrema_form = extrema_form == 1 ? 1 : 0;
+    return SIFT_B200_OK;
+}
+
+long sift_b200_graphs_built(const sift_b200_ctx* c) { return c ? c->graphs_built : 0; }
 
 long sift_b200_launch_count(const sift_b200_ctx* c) { return c ? c->launches : 0; }
 

@@ -7,6 +7,7 @@
 // results are independent of the order in which lanes arrive: the whole detect call is
 // bit-reproducible although list compaction uses atomics (the final order is re-established by an
 // exact sort on the reference's own comparison key).
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -169,6 +170,111 @@ k_extrema(const OctaveDesc oct, int octave, float thr, Cand* __restrict__ cands,
                     if (m) extrema_emit(m, hit[z - 1], lane, x, y, z, octave, cands, cap, counters);
                 }
             }
+        }
+    }
+}
+
+// Second form of the same scan, FOUR columns per lane (the default).  The 27-cell max / min is separable, so it is
+// reduced vertically first (the three window rows are the raw float4 rows themselves, kept in a 4-slot rotating
+// register window: three rows in use, the fourth in flight), then across the three planes, and only the
+// NZ = ND - 2 reduced rows go through the warp shuffles of the horizontal step (2 shuffles per quantity per FOUR
+// pixels instead of per pixel).  A warp covers 128 loaded / 124 tested columns per row with one LDG.128 per plane;
+// ~37 instructions per pixel against ~105 of the one-column form.  Same candidate set (the list is unordered).
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+constexpr int EX4_STRIP = 124;   // tested columns per warp: 128 loaded minus 2 on each side (kept a multiple of 4)
+#ifndef SB_EX4_CTAS
+#define SB_EX4_CTAS 3
+#endif
+template <int ND>
+__global__ void __launch_bounds__(128, SB_EX4_CTAS)
+k_extrema4(const OctaveDesc oct, int octave, float thr, int rows, Cand* __restrict__ cands, int cap,
+           Counters* __restrict__ counters) {
+    constexpr int NZ = ND - 2;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = oct.w, h = oct.h, pitch = oct.pitch;
+    const int x0 = blockIdx.x * EX4_STRIP - 4 + 4 * lane;   // this lane's first column; the strip tests lane positions 2..125
+    const int ys = 1 + (blockIdx.y * 4 + warp) * rows;      // first tested row of this warp
+    if (ys > h - 2) return;
+    const int ye = min(ys + rows - 1, h - 2);
+    // lanes hanging over the left / right end of the row load a clamped (wrong, unused) position: their columns are
+    // neither tested nor neighbours of a tested column
+    const unsigned xl = (unsigned)min(max(x0, 0), pitch - 4);
+    unsigned ok = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int pos = 4 * lane + c, x = x0 + c;
+        if (pos >= 2 && pos <= EX4_STRIP + 1 && x >= 1 && x <= w - 2) ok |= 1u << c;
+    }
+    float4 win[4][ND];
+    auto fetch = [&](int y, int slot) {
+        const unsigned off = (unsigned)min(y, h - 1) * (unsigned)pitch + xl;   // a plane has < 2^31 pixels
+#pragma unroll
+        for (int z = 0; z < ND; ++z) win[slot][z] = ldg4(oct.D[z] + off);
+    };
+    auto test_row = [&](const float4 (&ra)[ND], const float4 (&rb)[ND], const float4 (&rc)[ND], int y) {
+        float vmx[3][4], vmn[3][4];   // vertical max / min of the last three planes
+        unsigned hits = 0;            // bit 4 (z - 1) + c
+#pragma unroll
+        for (int p = 0; p < ND; ++p) {
+            float* mx = vmx[p % 3];
+            float* mn = vmn[p % 3];
+            mx[0] = fmax3(ra[p].x, rb[p].x, rc[p].x); mn[0] = fmin3(ra[p].x, rb[p].x, rc[p].x);
+            mx[1] = fmax3(ra[p].y, rb[p].y, rc[p].y); mn[1] = fmin3(ra[p].y, rb[p].y, rc[p].y);
+            mx[2] = fmax3(ra[p].z, rb[p].z, rc[p].z); mn[2] = fmin3(ra[p].z, rb[p].z, rc[p].z);
+            mx[3] = fmax3(ra[p].w, rb[p].w, rc[p].w); mn[3] = fmin3(ra[p].w, rb[p].w, rc[p].w);
+            if (p < 2) continue;
+            const int z = p - 1;
+            float zx[4], zn[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                zx[c] = fmax3(vmx[0][c], vmx[1][c], vmx[2][c]);
+                zn[c] = fmin3(vmn[0][c], vmn[1][c], vmn[2][c]);
+            }
+            const float lx = __shfl_up_sync(FULL, zx[3], 1), rx = __shfl_down_sync(FULL, zx[0], 1);
+            const float ln = __shfl_up_sync(FULL, zn[3], 1), rn = __shfl_down_sync(FULL, zn[0], 1);
+            const float hx[4] = {fmax3(lx, zx[0], zx[1]), fmax3(zx[0], zx[1], zx[2]), fmax3(zx[1], zx[2], zx[3]),
+                                 fmax3(zx[2], zx[3], rx)};
+            const float hn[4] = {fmin3(ln, zn[0], zn[1]), fmin3(zn[0], zn[1], zn[2]), fmin3(zn[1], zn[2], zn[3]),
+                                 fmin3(zn[2], zn[3], rn)};
+            const float cv[4] = {rb[z].x, rb[z].y, rb[z].z, rb[z].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (fabsf(cv[c]) > thr && (cv[c] == hx[c] || cv[c] == hn[c])) hits |= 1u << (4 * (z - 1) + c);
+        }
+        unsigned mask = 0;
+#pragma unroll
+        for (int z = 0; z < NZ; ++z) mask |= ok << (4 * z);
+        hits &= mask;
+        if (__ballot_sync(FULL, hits != 0)) {   // ~a third of the 124-pixel rows hold an extremum
+            const int cnt = __popc(hits);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += t;
+            }
+            int slot = 0;
+            if (lane == 31) slot = atomicAdd(&counters->n_extrema, incl);
+            slot = __shfl_sync(FULL, slot, 31) + incl - cnt;
+            while (hits) {
+                const int b = __ffs(hits) - 1;
+                hits &= hits - 1;
+                if (slot < cap) cands[slot] = Cand{x0 + (b & 3), y, 1 + (b >> 2), octave};
+                ++slot;
+            }
+        }
+    };
+    fetch(ys - 1, 0); fetch(ys, 1); fetch(ys + 1, 2);
+#pragma unroll 1
+    for (int y0 = ys; y0 <= ye; y0 += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {   // unrolled by the slot count: the window rotates without register moves
+            const int y = y0 + j;
+            if (y > ye) break;
+            fetch(y + 2, (j + 3) & 3);   // in flight while this row and the next are tested
+            test_row(win[j & 3], win[(j + 1) & 3], win[(j + 2) & 3], y);
         }
     }
 }
@@ -764,24 +870,37 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
 
 }  // namespace
 
-cudaError_t launch_range(const float* px, size_t n, float* range, cudaStream_t s) {
+cudaError_t launch_range(const float* px, size_t n, float* range, int sm_count, cudaStream_t s) {
     const float init[2] = {INFINITY, -INFINITY};
     cudaError_t e = cudaMemcpyAsync(range, init, sizeof init, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return e;
-    k_range<<<148 * 4, 256, 0, s>>>(px, n, range);
+    k_range<<<sm_count * 4, 256, 0, s>>>(px, n, range);
     return cudaGetLastError();
 }
 
 cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int border, int threshold, Cand* cands,
-                           int cap, Counters* counters, cudaStream_t s) {
+                           int cap, Counters* counters, int form, cudaStream_t s) {
     if (oct.w < 2 * border + 1 || oct.h < 2 * border + 1) return cudaSuccess;
     if (border != 1) {
         dim3 grid((oct.w - 2 * border + 255) / 256, oct.h - 2 * border);
         k_extrema_window<<<grid, 256, 0, s>>>(oct, octave, dogs, border, (float)threshold, cands, cap, counters);
         return cudaGetLastError();
     }
-    // rows per warp: 32 on large octaves, 8 on mid-size ones, 2 on tiny ones (more warps, shorter serial walks)
     const long long px = (long long)oct.w * oct.h;
+    if (form != 1) {   // form 1: the one-column-per-lane kernel (kept for comparison; same candidate set)
+        // rows per warp: long walks on large octaves (2 halo rows each), short ones where the grid would not fill the GPU
+        const int rows = px >= (16ll << 20) ? 32 : px >= (1ll << 20) ? 16 : px >= (1ll << 16) ? 4 : 2;
+        dim3 grid(oct.w / EX4_STRIP + 1, (oct.h - 2 + 4 * rows - 1) / (4 * rows));
+        switch (dogs) {
+            case 4: k_extrema4<4><<<grid, 128, 0, s>>>(oct, octave, (float)threshold, rows, cands, cap, counters); break;
+            case 5: k_extrema4<5><<<grid, 128, 0, s>>>(oct, octave, (float)threshold, rows, cands, cap, counters); break;
+            case 6: k_extrema4<6><<<grid, 128, 0, s>>>(oct, octave, (float)threshold, rows, cands, cap, counters); break;
+            case 7: k_extrema4<7><<<grid, 128, 0, s>>>(oct, octave, (float)threshold, rows, cands, cap, counters); break;
+            default: return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
+    // rows per warp: 32 on large octaves, 8 on mid-size ones, 2 on tiny ones (more warps, shorter serial walks)
     const int rows = px >= (16ll << 20) ? 32 : px >= (1ll << 18) ? 8 : 2;
     dim3 grid((oct.w - 2 + 29) / 30, (oct.h - 2 + 8 * rows - 1) / (8 * rows));
 #define SB_EX(ND)                                                                                                  \
@@ -799,30 +918,30 @@ cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int bord
 }
 
 cudaError_t launch_refine(const PyramidDesc* d_pyr, const Cand* cands, KpCore* raw, Counters* counters,
-                          const StageParams& sp, cudaStream_t s) {
-    k_refine<<<148 * 16, 128, 0, s>>>(d_pyr, cands, raw, counters, sp);
+                          const StageParams& sp, int sm_count, cudaStream_t s) {
+    k_refine<<<sm_count * 16, 128, 0, s>>>(d_pyr, cands, raw, counters, sp);
     return cudaGetLastError();
 }
 
 cudaError_t launch_orient(const PyramidDesc* d_pyr, const KpCore* raw, KpCore* oriented, Counters* counters,
-                          const StageParams& sp, cudaStream_t s) {
+                          const StageParams& sp, int sm_count, cudaStream_t s) {
     if (sp.num_bins == kOriBins)
-        k_orient<kOriBins><<<148 * SB_ORI_CTAS, 256, 0, s>>>(d_pyr, raw, oriented, counters, sp);
+        k_orient<kOriBins><<<sm_count * SB_ORI_CTAS, 256, 0, s>>>(d_pyr, raw, oriented, counters, sp);
     else
-        k_orient<0><<<148 * SB_ORI_CTAS, 256, 0, s>>>(d_pyr, raw, oriented, counters, sp);
+        k_orient<0><<<sm_count * SB_ORI_CTAS, 256, 0, s>>>(d_pyr, raw, oriented, counters, sp);
     return cudaGetLastError();
 }
 
 cudaError_t launch_sort_dedup(const KpCore* oriented, Counters* counters, const SortScratch& ss,
-                              const StageParams& sp, cudaStream_t s, int* launches) {
+                              const StageParams& sp, int sm_count, cudaStream_t s, int* launches) {
     cudaError_t e;
     k_sort_clear<<<(ss.nb + 256) / 256, 256, 0, s>>>(ss);
-    k_bucket_count<<<148 * 2, 256, 0, s>>>(oriented, counters, ss, sp.cap_oriented);
+    k_bucket_count<<<sm_count * 2, 256, 0, s>>>(oriented, counters, ss, sp.cap_oriented);
     k_scan<<<1, 1024, 0, s>>>(ss.bucket_cnt, ss.bucket_off, ss.nb, nullptr);
-    k_bucket_scatter<<<148 * 2, 256, 0, s>>>(oriented, counters, ss, sp.cap_oriented);
-    k_bucket_rank<<<148 * 4, 256, 0, s>>>(oriented, ss);
+    k_bucket_scatter<<<sm_count * 2, 256, 0, s>>>(oriented, counters, ss, sp.cap_oriented);
+    k_bucket_rank<<<sm_count * 4, 256, 0, s>>>(oriented, ss);
     k_scan<<<1, 1024, 0, s>>>(ss.uniq_cnt, ss.uniq_off, ss.nb, &counters->n_final);
-    k_bucket_gather<<<148 * 2, 256, 0, s>>>(ss);
+    k_bucket_gather<<<sm_count * 2, 256, 0, s>>>(ss);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (launches) *launches += 7;
     return cudaSuccess;
@@ -830,8 +949,8 @@ cudaError_t launch_sort_dedup(const KpCore* oriented, Counters* counters, const 
 
 cudaError_t launch_describe(const PyramidDesc* d_pyr, const KpCore* oriented, const int* final_order,
                             Counters* counters, uint8_t* records, uint8_t* desc, int cap_final,
-                            const StageParams& sp, cudaStream_t s) {
-    k_describe<<<148 * DESC_CTAS, DESC_WARPS * 32, 0, s>>>(d_pyr, oriented, final_order, counters, records, desc, cap_final, sp);
+                            const StageParams& sp, int sm_count, cudaStream_t s) {
+    k_describe<<<sm_count * DESC_CTAS, DESC_WARPS * 32, 0, s>>>(d_pyr, oriented, final_order, counters, records, desc, cap_final, sp);
     return cudaGetLastError();
 }
 

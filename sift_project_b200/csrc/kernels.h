@@ -6,16 +6,19 @@ namespace sb {
 
 // pyramid.cu
 cudaError_t pyramid_init();
+// centre: the value subtracted from every pixel on the way in (the scale space is linear and DC-preserving, and every
+// consumer takes differences, so the result is the same with 2-4x smaller FP32 rounding steps).  u8: a host
+// constant; f32: the midpoint of the device-side (min, max) in `range` when centred, else 0.
 cudaError_t launch_prepare_u8(const uint8_t* src, int sw, int sh, int ch, float* dst, int dw, int dh,
-                              int dpitch, int doubled, cudaStream_t s);
+                              int dpitch, int doubled, float centre, cudaStream_t s);
 cudaError_t launch_prepare_f32(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh,
-                               int dpitch, int doubled, cudaStream_t s);
+                               int dpitch, int doubled, const float* centre_range, cudaStream_t s);
 cudaError_t launch_blur(const float* in, float* out, float* dog, float* dec, int w, int h, int pitch,
                         int dec_w, int dec_h, int dec_pitch, const BlurTaps& taps, cudaStream_t s);
 
 bool input_fused_supported(int channels, const BlurTaps& taps);
 cudaError_t launch_input_u8(const uint8_t* src, int sw, int sh, float* dst, int w, int h, int pitch, int doubled,
-                            const BlurTaps& taps, cudaStream_t s);
+                            const BlurTaps& taps, float centre, cudaStream_t s);
 bool cascade_supported(const BlurTaps* taps);
 cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, float* dec, int dec_w, int dec_h,
                                 int dec_pitch, bool keep_all, int sm_count, int mode, int part, cudaStream_t s);
@@ -33,18 +36,18 @@ struct SortScratch {
     int* sorted;        // [cap_oriented]
     int* final_order;   // [cap_oriented]
 };
-cudaError_t launch_range(const float* px, size_t n, float* range, cudaStream_t s);
+cudaError_t launch_range(const float* px, size_t n, float* range, int sm_count, cudaStream_t s);
 cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int border, int threshold, Cand* cands,
-                           int cap, Counters* counters, cudaStream_t s);
+                           int cap, Counters* counters, int form, cudaStream_t s);
 cudaError_t launch_refine(const PyramidDesc* d_pyr, const Cand* cands, KpCore* raw,
-                          Counters* counters, const StageParams& sp, cudaStream_t s);
+                          Counters* counters, const StageParams& sp, int sm_count, cudaStream_t s);
 cudaError_t launch_orient(const PyramidDesc* d_pyr, const KpCore* raw, KpCore* oriented,
-                          Counters* counters, const StageParams& sp, cudaStream_t s);
+                          Counters* counters, const StageParams& sp, int sm_count, cudaStream_t s);
 cudaError_t launch_sort_dedup(const KpCore* oriented, Counters* counters, const SortScratch& ss,
-                              const StageParams& sp, cudaStream_t s, int* launches);
+                              const StageParams& sp, int sm_count, cudaStream_t s, int* launches);
 cudaError_t launch_describe(const PyramidDesc* d_pyr, const KpCore* oriented, const int* final_order,
                             Counters* counters, uint8_t* records, uint8_t* desc, int cap_final,
-                            const StageParams& sp, cudaStream_t s);
+                            const StageParams& sp, int sm_count, cudaStream_t s);
 
 // match_simt.cu
 struct MatchScratch {

@@ -450,7 +450,7 @@ struct InputGeom {
 template <bool DOUBLED, int TWI, int THI, int NTI, int MINBI>
 __global__ void __launch_bounds__(NTI, MINBI)
 k_input_u8(const uint8_t* __restrict__ src, int sw, int sh, float* __restrict__ dst, int w, int h, int pitch,
-           const BlurTaps taps) {
+           const BlurTaps taps, const float centre) {
     constexpr int IN_W0 = InputGeom<TWI, THI>::W0, IN_H0 = InputGeom<TWI, THI>::H0;
     constexpr int TW = TWI, TH = THI, CT = NTI;
     extern __shared__ __align__(16) float smem[];
@@ -466,8 +466,9 @@ k_input_u8(const uint8_t* __restrict__ src, int sw, int sh, float* __restrict__ 
             const int br = idx / (IN_W0 / 2), bc = idx - br * (IN_W0 / 2);
             const int x0 = sx0 + bc, y0 = sy0 + br;
             const int x1 = min(x0 + 1, sw - 1), y1 = min(y0 + 1, sh - 1);
-            const float p = __ldg(src + (size_t)y0 * sw + x0), q = __ldg(src + (size_t)y0 * sw + x1);
-            const float t = __ldg(src + (size_t)y1 * sw + x0), u = __ldg(src + (size_t)y1 * sw + x1);
+            // (pixel - centre: integers below 2^8, so the quarter-integer averages below stay exact)
+            const float p = __ldg(src + (size_t)y0 * sw + x0) - centre, q = __ldg(src + (size_t)y0 * sw + x1) - centre;
+            const float t = __ldg(src + (size_t)y1 * sw + x0) - centre, u = __ldg(src + (size_t)y1 * sw + x1) - centre;
             const float top = p * 0.5f + q * 0.5f, bot = t * 0.5f + u * 0.5f;
             *reinterpret_cast<float2*>(sA + (2 * br) * IN_W0 + 2 * bc) = make_float2(p, top);
             *reinterpret_cast<float2*>(sA + (2 * br + 1) * IN_W0 + 2 * bc) =
@@ -482,12 +483,12 @@ k_input_u8(const uint8_t* __restrict__ src, int sw, int sh, float* __restrict__ 
             const int x0 = X >> 1, y0 = Y >> 1;
             const int x1 = min(x0 + 1, sw - 1), y1 = min(y0 + 1, sh - 1);
             const float fx = (X & 1) ? 0.5f : 0.0f, fy = (Y & 1) ? 0.5f : 0.0f;
-            const float p = __ldg(src + (size_t)y0 * sw + x0), q = __ldg(src + (size_t)y0 * sw + x1);
-            const float t = __ldg(src + (size_t)y1 * sw + x0), u = __ldg(src + (size_t)y1 * sw + x1);
+            const float p = __ldg(src + (size_t)y0 * sw + x0) - centre, q = __ldg(src + (size_t)y0 * sw + x1) - centre;
+            const float t = __ldg(src + (size_t)y1 * sw + x0) - centre, u = __ldg(src + (size_t)y1 * sw + x1) - centre;
             const float top = p * (1.f - fx) + q * fx, bot = t * (1.f - fx) + u * fx;
             v = top * (1.f - fy) + bot * fy;
         } else {
-            v = (float)__ldg(src + (size_t)Y * sw + X);
+            v = (float)__ldg(src + (size_t)Y * sw + X) - centre;
         }
         sA[idx] = v;
     }
@@ -510,10 +511,12 @@ k_input_u8(const uint8_t* __restrict__ src, int sw, int sh, float* __restrict__ 
 // FP64 with the reference's association order and rounded once.
 template <typename T>
 __global__ void k_prepare(const T* __restrict__ src, int sw, int sh, int ch, float* __restrict__ dst,
-                          int dw, int dh, int dpitch, int doubled) {
+                          int dw, int dh, int dpitch, int doubled, float centre_const,
+                          const float* __restrict__ centre_range) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= dw || y >= dh) return;
+    const double centre = centre_range ? 0.5 * ((double)centre_range[0] + (double)centre_range[1]) : (double)centre_const;
     auto gray = [&](int sx, int sy) -> double {
         const T* p = src + ((size_t)sy * sw + sx) * ch;
         if (ch == 1) return (double)p[0];
@@ -530,23 +533,23 @@ __global__ void k_prepare(const T* __restrict__ src, int sw, int sh, int ch, flo
         const double bot = gray(x0, y1) * (1 - fx) + gray(x1, y1) * fx;
         v = top * (1 - fy) + bot * fy;
     }
-    dst[(size_t)y * dpitch + x] = (float)v;
+    dst[(size_t)y * dpitch + x] = (float)(v - centre);
 }
 
 __global__ void k_prepare_gray_u8(const uint8_t* __restrict__ src, int sw, int sh,
-                                  float* __restrict__ dst, int dw, int dh, int dpitch, int doubled) {
+                                  float* __restrict__ dst, int dw, int dh, int dpitch, int doubled, float centre) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= dw || y >= dh) return;
     float v;
     if (!doubled) {
-        v = (float)src[(size_t)y * sw + x];
+        v = (float)src[(size_t)y * sw + x] - centre;
     } else {
         const int x0 = x >> 1, y0 = y >> 1;
         const int x1 = min(x0 + 1, sw - 1), y1 = min(y0 + 1, sh - 1);
         const float fx = (x & 1) ? 0.5f : 0.0f, fy = (y & 1) ? 0.5f : 0.0f;
-        const float a = src[(size_t)y0 * sw + x0], b = src[(size_t)y0 * sw + x1];
-        const float c = src[(size_t)y1 * sw + x0], d = src[(size_t)y1 * sw + x1];
+        const float a = src[(size_t)y0 * sw + x0] - centre, b = src[(size_t)y0 * sw + x1] - centre;
+        const float c = src[(size_t)y1 * sw + x0] - centre, d = src[(size_t)y1 * sw + x1] - centre;
         const float top = a * (1.f - fx) + b * fx, bot = c * (1.f - fx) + d * fx;
         v = top * (1.f - fy) + bot * fy;  // exact: quarter-integers below 2^10
     }
@@ -616,14 +619,14 @@ cudaError_t launch_blur(const float* in, float* out, float* dog, float* dec, int
 bool input_fused_supported(int channels, const BlurTaps& taps) { return channels == 1 && taps.radius == IN_R; }
 
 cudaError_t launch_input_u8(const uint8_t* src, int sw, int sh, float* dst, int w, int h, int pitch, int doubled,
-                            const BlurTaps& taps, cudaStream_t s) {
+                            const BlurTaps& taps, float centre, cudaStream_t s) {
     // tile shapes measured at 4K (ms): 128x64 / 512 threads / 2 per SM 0.088, 128x32 / 256 / 4 0.079,
     // 128x32 / 512 / 3 0.077, 64x64 / 256 / 4 0.077, 128x16 / 256 / 6 0.078
     dim3 grid((w + 127) / 128, (h + 31) / 32);
     if (doubled)
-        k_input_u8<true, 128, 32, 512, 3><<<grid, 512, InputGeom<128, 32>::kSmem, s>>>(src, sw, sh, dst, w, h, pitch, taps);
+        k_input_u8<true, 128, 32, 512, 3><<<grid, 512, InputGeom<128, 32>::kSmem, s>>>(src, sw, sh, dst, w, h, pitch, taps, centre);
     else
-        k_input_u8<false, 128, 32, 512, 3><<<grid, 512, InputGeom<128, 32>::kSmem, s>>>(src, sw, sh, dst, w, h, pitch, taps);
+        k_input_u8<false, 128, 32, 512, 3><<<grid, 512, InputGeom<128, 32>::kSmem, s>>>(src, sw, sh, dst, w, h, pitch, taps, centre);
     return cudaGetLastError();
 }
 
@@ -668,19 +671,19 @@ cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, floa
 }
 
 cudaError_t launch_prepare_u8(const uint8_t* src, int sw, int sh, int ch, float* dst, int dw, int dh,
-                              int dpitch, int doubled, cudaStream_t s) {
+                              int dpitch, int doubled, float centre, cudaStream_t s) {
     dim3 block(32, 8), grid((dw + 31) / 32, (dh + 7) / 8);
     if (ch == 1)
-        k_prepare_gray_u8<<<grid, block, 0, s>>>(src, sw, sh, dst, dw, dh, dpitch, doubled);
+        k_prepare_gray_u8<<<grid, block, 0, s>>>(src, sw, sh, dst, dw, dh, dpitch, doubled, centre);
     else
-        k_prepare<uint8_t><<<grid, block, 0, s>>>(src, sw, sh, ch, dst, dw, dh, dpitch, doubled);
+        k_prepare<uint8_t><<<grid, block, 0, s>>>(src, sw, sh, ch, dst, dw, dh, dpitch, doubled, centre, nullptr);
     return cudaGetLastError();
 }
 
 cudaError_t launch_prepare_f32(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh,
-                               int dpitch, int doubled, cudaStream_t s) {
+                               int dpitch, int doubled, const float* centre_range, cudaStream_t s) {
     dim3 block(32, 8), grid((dw + 31) / 32, (dh + 7) / 8);
-    k_prepare<float><<<grid, block, 0, s>>>(src, sw, sh, ch, dst, dw, dh, dpitch, doubled);
+    k_prepare<float><<<grid, block, 0, s>>>(src, sw, sh, ch, dst, dw, dh, dpitch, doubled, 0.f, centre_range);
     return cudaGetLastError();
 }
 

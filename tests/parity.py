@@ -63,3 +63,41 @@ def set_diff_report(a, b):
     sa = {tuple(r) for r in np.asarray(a).tolist()}
     sb = {tuple(r) for r in np.asarray(b).tolist()}
     return len(sa & sb), len(sa - sb), len(sb - sa)
+
+
+def descriptor_parity(got, want, gi, wi, run):
+    """north_star: "descriptor max-abs difference of at most 1 ulp after the reference's quantisation".
+
+    The descriptor STAGE meets that bar on identical keypoints (test_descriptor_stage_on_reference_keypoints).
+    End to end, a paired keypoint whose own (x, y, size, pori) differs from the reference's inside the pairing
+    tolerances -- one orientation-histogram sample on the other side of a hard bin edge moves the interpolated
+    peak by ~1e-3 rad -- gets a descriptor of a slightly different patch.  Every pair that differs by more than one
+    level is therefore ATTRIBUTED here: the CPU oracle (`run`, created with keep_pyramid) recomputes the descriptor
+    from the GPU's own keypoint record; the GPU descriptor must be within one level of THAT, and the keypoint
+    record must really differ from the reference's.  Returns the plain report plus
+      n_outliers      pairs with a difference > 1 level
+      unexplained     outliers whose keypoint record is bit-identical to the reference's (must be 0)
+      max_attributed  max difference to the oracle's descriptor of the GPU's own keypoint, over the outliers
+                      (must be <= 1); 0 when there are none."""
+    rep = descriptor_report(got, want, gi, wi)
+    rep.update(n_outliers=0, unexplained=0, max_attributed=0)
+    if len(gi) == 0:
+        return rep
+    d = np.abs(got["desc"][gi].astype(np.int16) - want["desc"][wi].astype(np.int16)).max(1)
+    out = np.nonzero(d > 1)[0]
+    rep["n_outliers"] = int(len(out))
+    if len(out) == 0:
+        return rep
+    g, w = got[gi[out]], want[wi[out]]
+    same = (g["x"] == w["x"]) & (g["y"] == w["y"]) & (g["size"] == w["size"]) & (g["pori"] == w["pori"])
+    rep["unexplained"] = int(same.sum())
+    redo = run.describe_given(g)
+    resid = np.abs(redo["desc"].astype(np.int16) - g["desc"].astype(np.int16)).max(1)
+    rep["max_attributed"] = int(resid.max())
+    rep["outlier_dpori_max"] = float(np.abs((g["pori"] - w["pori"] + np.pi) % (2 * np.pi) - np.pi).max())
+    return rep
+
+
+def assert_descriptor_parity(rep):
+    assert rep["unexplained"] == 0, rep
+    assert rep["max_attributed"] <= 1, rep

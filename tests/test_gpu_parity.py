@@ -83,10 +83,108 @@ def test_stage_lists_match_reference_golden(ctx, synth):
         REPORT[f"synth_{key}"] = dict(n_gpu=len(got), n_ref=len(synth[key]), recall=rec, precision=prec)
         assert rec >= 0.995 and prec >= 0.995
     rec, prec, gi, wi = P.recall_precision(final, synth["final"])
-    rep = P.descriptor_report(final, synth["final"], gi, wi)
+    rep = P.descriptor_parity(final, synth["final"], gi, wi, O.Run(O.best(), img, keep_pyramid=True))
     REPORT["synth_final"] = dict(n_gpu=len(final), n_ref=len(synth["final"]), recall=rec, precision=prec, desc=rep)
     assert rec >= 0.995 and prec >= 0.995
     assert rep["frac_le1"] >= 0.99
+    P.assert_descriptor_parity(rep)
+
+
+@pytest.mark.parametrize("shape_seed", [(192, 256, 42), (300, 400, 31), (480, 640, 77)])
+def test_descriptor_stage_on_reference_keypoints(ctx, shape_seed):
+    """compute_descriptors (sift.cpp:610-682) + update_histogram (:541-571) + convert_hist_to_desc (:576-603) in
+    isolation: the GPU stage on the REFERENCE's own final keypoints (bit-identical x, y, size, pori), over the
+    GPU's FP32 scale space, against the reference's descriptors.  north_star bar: max-abs <= 1 level, every
+    keypoint, no exceptions."""
+    h, w, seed = shape_seed
+    img = O.synth_image(h, w, seed=seed)
+    run = O.Run(O.best(), img, keep_pyramid=False)
+    want = run.keypoints(2)
+    ctx.detect(img)
+    got = ctx.describe_given(want)
+    assert len(want) > 200
+    for f in ("x", "y", "size", "pori", "octave", "layer"):
+        assert np.array_equal(got[f], want[f]), f
+    d = np.abs(got["desc"].astype(np.int16) - want["desc"].astype(np.int16))
+    REPORT[f"desc_stage_{w}x{h}"] = dict(n=len(want), max=int(d.max()), frac_exact=float((d.max(1) == 0).mean()),
+                                         frac_bins_off_by_one=float((d == 1).mean()))
+    assert d.max() <= 1
+
+
+def test_orientation_stage_on_reference_keypoints(ctx):
+    """compute_orientations (sift.cpp:447-533) in isolation: the GPU stage on the reference's raw keypoints.  The
+    36-bin histogram rounds every sample's angle to a bin (sift.cpp:489), so a sample within the FP32 scale
+    space's error of a bin edge may land next door and shift the interpolated peak slightly: same peaks, pori
+    within the pairing tolerance, and bit-identical x / y / size."""
+    img = O.synth_image(300, 400, seed=31)
+    run = O.Run(O.best(), img, keep_pyramid=False)
+    raw, want = run.keypoints(0), run.keypoints(1)
+    ctx.detect(img)
+    got = ctx.orient_given(raw)
+    rec, prec, gi, wi = P.recall_precision(got, want)
+    dp = np.abs((got["pori"][gi] - want["pori"][wi] + np.pi) % (2 * np.pi) - np.pi)
+    REPORT["orient_stage"] = dict(n_gpu=len(got), n_ref=len(want), recall=rec, precision=prec,
+                                  pori_exact=float((dp == 0).mean()), pori_lt_1e6=float((dp < 1e-6).mean()),
+                                  pori_max=float(dp.max()))
+    assert rec >= 0.995 and prec >= 0.995
+    for f in ("x", "y", "size"):
+        assert np.array_equal(got[f][gi], want[f][wi]), f
+    assert np.quantile(dp, 0.9) < 1e-5
+
+
+def test_centred_scale_space_is_closer_to_the_fp64_reference(ctx, synth):
+    """The scale space is stored relative to the input's mid level (sift_b200_debug_launch_plan): same planes up to
+    rounding, with a smaller error against the FP64 oracle than the uncentred FP32 form."""
+    img = synth["image"]
+    run = O.Run(O.port(), img, keep_pyramid=True)
+    err = {}
+    for centred in (0, 1):
+        ctx.launch_plan(centred=centred)
+        ctx.detect(img)
+        e = []
+        for o in range(3):
+            for l in (1, 2, 3):
+                e.append(np.abs(ctx.gaussian(o, l).astype(np.float64) - run.gaussian(o, l)).max())
+            for l in range(5):
+                e.append(np.abs(ctx.dog(o, l).astype(np.float64) - run.dog(o, l)).max())
+        err[centred] = float(max(e))
+    ctx.launch_plan(centred=1)
+    REPORT["centred_vs_plain_max_abs_err"] = err
+    assert err[1] <= err[0] and err[1] < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(192, 256), (301, 517), (97, 1030), (768, 1024), (125, 124), (126, 249)])
+def test_extrema_kernel_forms_find_the_same_set(ctx, shape):
+    """detect_octave_extrema (sift.cpp:264-291): the four-columns-per-lane kernel (default) and the one-column
+    kernel return the same candidate set -- widths around the 124-column strip edge included -- and the same
+    final records."""
+    h, w = shape
+    img = O.synth_image(h, w, seed=h + w)
+    ctx.launch_plan(extrema_form=1)
+    ref = ctx.detect(img)
+    ex1 = ctx.extrema()
+    ctx.launch_plan(extrema_form=0)
+    got = ctx.detect(img)
+    ex4 = ctx.extrema()
+    assert len(ex1) > 50
+    assert P.set_diff_report(ex4, ex1)[1:] == (0, 0)
+    assert len(ex4) == len(ex1)            # no duplicates either
+    assert got.tobytes() == ref.tobytes()
+
+
+def test_graph_replay_equals_plain_launches(ctx, synth):
+    """The CUDA-graph launch plan (forked octave chain) and plain single-stream launches run the same kernels on
+    the same data: identical bytes; one graph per image size / parameter set, re-captured only on a change."""
+    img, img2 = synth["image"], O.synth_image(200, 300, seed=9)
+    ctx.launch_plan(use_graph=0)
+    ref, ref2 = ctx.detect(img), ctx.detect(img2)
+    ctx.launch_plan(use_graph=1)
+    g0 = ctx.graphs_built
+    a = ctx.detect(img); b = ctx.detect(img); c = ctx.detect(img2); d = ctx.detect(img, peak_ratio=0.7); e = ctx.detect(img)
+    assert ctx.graphs_built - g0 == 4          # img, img2, img with other parameters, img again
+    assert a.tobytes() == ref.tobytes() and b.tobytes() == ref.tobytes() and e.tobytes() == ref.tobytes()
+    assert c.tobytes() == ref2.tobytes()
+    assert len(d) != len(a)
 
 
 def test_output_order_is_the_reference_sort(ctx, synth):
@@ -114,13 +212,14 @@ def test_config1_detect(ctx, config1, golden_dir, name):
     want = config1[name + "_final"]
     st = ctx.stats()
     rec, prec, gi, wi = P.recall_precision(got, want)
-    rep = P.descriptor_report(got, want, gi, wi)
+    rep = P.descriptor_parity(got, want, gi, wi, O.Run(O.best(), px, keep_pyramid=True))
     REPORT[f"config1_{name}"] = dict(stats=st, n_ref=len(want), recall=rec, precision=prec, desc=rep,
                                      ref_extrema=len(config1[name + "_extrema"]), ref_raw=len(config1[name + "_raw"]))
     assert st["octaves"] == 8
     assert abs(st["extrema"] - len(config1[name + "_extrema"])) <= 0.005 * len(config1[name + "_extrema"])
     assert rec >= 0.995 and prec >= 0.995
     assert rep["frac_le1"] >= 0.99
+    P.assert_descriptor_parity(rep)
 
 
 def test_config1_match_on_reference_descriptors(ctx, config1):
@@ -201,13 +300,14 @@ def test_undoubled_and_f32_and_rgb_inputs(ctx):
     for tag, img, doubled in (("gray_undoubled", g, False), ("rgb_doubled", rgb, True),
                               ("rgb_undoubled", rgb, False), ("f32_gray", g.astype(np.float32) * 0.5 + 17.25, True)):
         got = ctx.detect(img, double_image_size=doubled)
-        run = O.Run(O.port(), img, doubled, keep_pyramid=False)
+        run = O.Run(O.port(), img, doubled, keep_pyramid=True)
         want = run.keypoints(2)
         rec, prec, gi, wi = P.recall_precision(got, want)
-        rep = P.descriptor_report(got, want, gi, wi)
+        rep = P.descriptor_parity(got, want, gi, wi, run)
         REPORT[tag] = dict(n_gpu=len(got), n_ref=len(want), recall=rec, precision=prec, desc=rep)
         assert len(want) > 50
         assert rec >= 0.99 and prec >= 0.99, tag
+        P.assert_descriptor_parity(rep)
 
 
 def test_max_octaves_extension_filters_octaves(ctx, synth):
@@ -437,18 +537,80 @@ def test_config2_1080p_four_octaves_vs_oracle():
     img = O.synth_image(1080, 1920, seed=1234)
     with S.SiftContext(1920, 1080) as c:
         got = c.detect(img, max_octaves=4)
-    run = O.Run(O.best(), img, keep_pyramid=False)
+    run = O.Run(O.best(), img, keep_pyramid=True)
     want = run.keypoints(2)
     want = want[want["octave"] < 4]
     rec, prec, gi, wi = P.recall_precision(got, want)
-    rep = P.descriptor_report(got, want, gi, wi)
+    rep = P.descriptor_parity(got, want, gi, wi, run)
     REPORT["config2_1080p_4oct"] = dict(n_gpu=len(got), n_ref=len(want), recall=rec, precision=prec, desc=rep)
     assert rec >= 0.995 and prec >= 0.995
     assert rep["frac_le1"] >= 0.99
+    P.assert_descriptor_parity(rep)
+
+
+def _large_golden(golden_dir, w, h, seed=1234):
+    """Final keypoints of the REAL reference at full size (tests/golden/make_golden_large.py)."""
+    z = np.load(os.path.join(golden_dir, f"synth_{w}x{h}_seed{seed}.npz"))
+    k = np.zeros(len(z["x"]), dtype=S.KP_DTYPE)
+    for f in ("x", "y", "size", "pori", "octave", "layer"):
+        k[f] = z[f]
+    stride = int(z["desc_stride"])
+    k["desc"][::stride] = z["desc"]
+    return k, z["counts"], stride, int(z["image_crc"])
+
+
+def _full_size_set_parity(tag, got, want, stride, ctx):
+    """Set-level comparison with the reference's keypoints (north_star: recall / precision >= 99.5 % at 0.01 px
+    and 1e-3 relative size), descriptors of the paired keypoints, and the descriptor stage alone on the
+    reference's own keypoints (max-abs <= 1 level)."""
+    rec, prec, gi, wi = P.recall_precision(got, want)
+    has = (wi % stride) == 0                       # pairs whose reference descriptor is in the fixture
+    rep = P.descriptor_report(got, want, gi[has], wi[has])
+    d = np.abs(got["desc"][gi[has]].astype(np.int16) - want["desc"][wi[has]].astype(np.int16)).max(1)
+    g, w_ = got[gi[has]][d > 1], want[wi[has]][d > 1]
+    same = (g["x"] == w_["x"]) & (g["y"] == w_["y"]) & (g["size"] == w_["size"]) & (g["pori"] == w_["pori"])
+    stage = ctx.describe_given(want[::stride])     # GPU descriptor stage on the reference's keypoints
+    sd = np.abs(stage["desc"].astype(np.int16) - want["desc"][::stride].astype(np.int16))
+    REPORT[tag] = dict(n_gpu=len(got), n_ref=len(want), recall=rec, precision=prec, desc=rep,
+                       n_outliers=int((d > 1).sum()), unexplained=int(same.sum()),
+                       desc_stage=dict(n=len(stage), max=int(sd.max()), frac_exact=float((sd.max(1) == 0).mean())))
+    assert rec >= 0.995 and prec >= 0.995, (rec, prec)
+    assert rep["frac_le1"] >= 0.99, rep
+    assert same.sum() == 0                          # a differing descriptor always comes with a differing keypoint
+    assert sd.max() <= 1
+
+
+def test_config3_4k_set_parity_vs_reference(golden_dir):
+    """Config 3's image 0 (3840x2160, generator D, seed 1234) against EVERY final keypoint of the real reference
+    (detect_keypoints_and_descriptors, sift.cpp:712-776: 27 536 keypoints, ~104 s of CPU, run once by
+    tests/golden/make_golden_large.py)."""
+    want, counts, stride, crc = _large_golden(golden_dir, 3840, 2160)
+    img = O.synth_image(2160, 3840, seed=1234)
+    assert int(img.astype(np.uint64).sum()) == crc      # same pixels as the fixture's run
+    with S.SiftContext(3840, 2160) as c:
+        got = c.detect(img)
+        st = c.stats()
+        assert [st["octaves"], len(got)] == [10, st["final_keypoints"]]
+        _full_size_set_parity("config3_4k_set", got, want, stride, c)
+    assert list(counts[1:]) == [157361, 21887, 27555, 27536]   # extrema / raw / oriented / final, SURVEY.md section 4
+
+
+def test_config4_8k_set_parity_vs_reference(golden_dir):
+    """Config 4 (7680x4320, 11 octaves, base 15360x8640): every final keypoint of the real reference; descriptors of
+    every 8th (fixture size)."""
+    want, counts, stride, crc = _large_golden(golden_dir, 7680, 4320)
+    img = O.synth_image(4320, 7680, seed=1234)
+    assert int(img.astype(np.uint64).sum()) == crc
+    with S.SiftContext(7680, 4320) as c:
+        got = c.detect(img)
+        st = c.stats()
+        assert st["octaves"] == 11 and st["base_width"] == 15360
+        assert abs(st["extrema"] - counts[1]) <= 0.005 * counts[1]
+        _full_size_set_parity("config4_8k_set", got, want, stride, c)
 
 
 def test_config4_8k_properties():
-    """Config 4 (7680x4320): too large for the CPU oracle in a test; size-independent properties."""
+    """Config 4 (7680x4320) on the benchmark's GPU generator: size-independent properties."""
     import torch
     sys_path_bench = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     import importlib.util
@@ -503,14 +665,16 @@ def test_non_default_arguments_vs_oracle(ctx, kw):
     of the fused cascade)."""
     img = O.synth_image(300, 400, seed=31)
     got = ctx.detect(img, **kw)
-    want = O.Run(O.best(), img, params=O.Params(**kw), keep_pyramid=False).keypoints(2)
+    run = O.Run(O.best(), img, params=O.Params(**kw), keep_pyramid=True)
+    want = run.keypoints(2)
     rec, prec, gi, wi = P.recall_precision(got, want)
-    rep = P.descriptor_report(got, want, gi, wi)
+    rep = P.descriptor_parity(got, want, gi, wi, run)
     REPORT["params_" + "_".join(f"{k}={v}" for k, v in sorted(kw.items()))[:60]] = dict(
         n_gpu=len(got), n_ref=len(want), recall=rec, precision=prec, desc=rep)
     assert len(want) > 30
     assert rec >= 0.99 and prec >= 0.99
     assert rep["frac_le1"] >= 0.98
+    P.assert_descriptor_parity(rep)
 
 
 @pytest.mark.parametrize("kw", [dict(intervals=2, contrast_threshold=0.05), dict(intervals=4, init_sigma=1.4, peak_ratio=0.75),
@@ -530,12 +694,13 @@ def test_other_interval_counts_vs_oracle(ctx, kw):
     worst = max(np.abs(ctx.dog(1, l) - run.dog(1, l)).max() for l in range(L - 1))
     assert worst < 3e-4
     rec, prec, gi, wi = P.recall_precision(got, want)
-    rep = P.descriptor_report(got, want, gi, wi)
+    rep = P.descriptor_parity(got, want, gi, wi, run)
     REPORT["intervals_" + "_".join(f"{k}={v}" for k, v in sorted(kw.items()))[:50]] = dict(
         n_gpu=len(got), n_ref=len(want), recall=rec, precision=prec, desc=rep, dog_err=worst)
     assert len(want) > 30
     assert rec >= 0.99 and prec >= 0.99
     assert rep["frac_le1"] >= 0.98
+    P.assert_descriptor_parity(rep)
 
 
 def test_random_shapes_fused_equals_per_level(ctx):
@@ -562,11 +727,13 @@ def test_random_small_images_vs_oracle(ctx, seed):
     h, w = int(rng.integers(90, 260)), int(rng.integers(90, 330))
     img = O.synth_image(h, w, seed=seed + 500)
     got = ctx.detect(img)
-    want = O.Run(O.best(), img, keep_pyramid=False).keypoints(2)
+    run = O.Run(O.best(), img, keep_pyramid=True)
+    want = run.keypoints(2)
     rec, prec, gi, wi = P.recall_precision(got, want)
-    rep = P.descriptor_report(got, want, gi, wi)
+    rep = P.descriptor_parity(got, want, gi, wi, run)
     assert rec >= 0.99 and prec >= 0.99, (h, w, rec, prec)
     assert rep["frac_le1"] >= 0.97
+    P.assert_descriptor_parity(rep)
 
 
 def test_noise_and_dense_texture_images(ctx):
@@ -597,17 +764,18 @@ def test_window_and_bin_counts_vs_oracle(ctx, kw):
     scan and in the refinement bounds; orientation histograms with other bin counts."""
     img = O.synth_image(300, 400, seed=35)
     got = ctx.detect(img, **kw)
-    run = O.Run(O.best(), img, params=O.Params(**kw), keep_pyramid=False)
+    run = O.Run(O.best(), img, params=O.Params(**kw), keep_pyramid=True)
     want = run.keypoints(2)
     both, only_gpu, only_ref = P.set_diff_report(ctx.extrema(), run.extrema().astype(np.int64))
     assert only_gpu + only_ref <= max(2, 0.005 * (both + only_ref))
     rec, prec, gi, wi = P.recall_precision(got, want)
-    rep = P.descriptor_report(got, want, gi, wi)
+    rep = P.descriptor_parity(got, want, gi, wi, run)
     REPORT["knobs_" + "_".join(f"{k}={v}" for k, v in sorted(kw.items()))[:50]] = dict(
         n_gpu=len(got), n_ref=len(want), recall=rec, precision=prec, desc=rep)
     assert len(want) > 30
     assert rec >= 0.99 and prec >= 0.99
     assert rep["frac_le1"] >= 0.98
+    P.assert_descriptor_parity(rep)
 
 
 @pytest.mark.parametrize("scale,offset", [(100.0, 0.0), (0.01, -1.0), (1.0, -128.0)])
@@ -617,10 +785,12 @@ def test_float_input_of_any_range(ctx, scale, offset):
     img = O.synth_image(240, 320, seed=41).astype(np.float32) * np.float32(scale) + np.float32(offset)
     kw = dict(contrast_threshold=0.04 * scale) if scale < 1 else {}
     got = ctx.detect(img, **kw)
-    want = O.Run(O.best(), img.astype(np.float64), params=O.Params(**kw), keep_pyramid=False).keypoints(2)
+    run = O.Run(O.best(), img.astype(np.float64), params=O.Params(**kw), keep_pyramid=True)
+    want = run.keypoints(2)
     rec, prec, gi, wi = P.recall_precision(got, want)
-    rep = P.descriptor_report(got, want, gi, wi)
+    rep = P.descriptor_parity(got, want, gi, wi, run)
     REPORT[f"f32_range_x{scale}_{offset}"] = dict(n_gpu=len(got), n_ref=len(want), recall=rec, precision=prec, desc=rep)
     assert len(want) > 50
     assert rec >= 0.99 and prec >= 0.99
     assert rep["frac_le1"] >= 0.97
+    P.assert_descriptor_parity(rep)
