@@ -137,7 +137,7 @@ def _cpu_worker_init():
         O.port()
 
 
-def _cpu_detect(img):
+def _cpu_detect(img, want_keypoints=False):
     O = _W["O"]
     t = time.perf_counter()
     if _W["kind"] == "reference":
@@ -145,13 +145,14 @@ def _cpu_detect(img):
         saved = os.dup(1)
         os.dup2(devnull, 1)  # silence the reference's per-stage std::cout chatter
         try:
-            n = len(O.ref_detect_public(img))
+            k = O.ref_detect_public(img)
         finally:
             os.dup2(saved, 1)
             os.close(devnull); os.close(saved)
     else:
-        n = len(O.Run(O.port(), img, keep_pyramid=False).keypoints(2))
-    return n, time.perf_counter() - t
+        k = O.Run(O.port(), img, keep_pyramid=False).keypoints(2)
+    dt = time.perf_counter() - t
+    return (len(k), dt, k) if want_keypoints else (len(k), dt)
 
 
 def cpu_kind():
@@ -203,18 +204,38 @@ def run_reference_arm(args):
     emit(line)
 
 
-def cpu_baseline_sample(img_u8_host):
-    """rank 0, N=1: the reference detect on one 1920x1080 crop (1/4 of a 4K image), 1 thread."""
+def cpu_baseline_sample(img_u8_host, device):
+    """rank 0, N=1: the reference detect on one 1920x1080 crop (1/4 of a 4K image), 1 thread -- and, since the
+    reference's keypoints of that crop are now at hand, the parity of the GPU path on the BENCHMARK's own pixels
+    (the torch-FFT generator, not the scipy one of the tests)."""
     import multiprocessing as mp
+    import sift_project_b200 as S
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity as P
     crop = np.ascontiguousarray(img_u8_host[:1080, :1920])
     ctx = mp.get_context("spawn")
     with ctx.Pool(1, initializer=_cpu_worker_init) as pool:
-        n, dt = pool.apply(_cpu_detect, (crop,))
+        n, dt, want = pool.apply(_cpu_detect, (crop, True))
     kind = cpu_kind()
-    return {"value": 0.25 / dt, "unit": "images/s", "cores": 1, "kind": kind,
-            "sample": f"one 1920x1080 crop (1/4 of the pixels) of batch image 0, {n} keypoints, {dt:.1f} s, "
-                      f"scaled by pixel count; "
-                      f"{'reference sources compiled copy-free (oracle/_ref)' if kind == 'reference' else 'oracle port'}"}
+    cpu = {"value": 0.25 / dt, "unit": "images/s", "cores": 1, "kind": kind,
+           "sample": f"one 1920x1080 crop (1/4 of the pixels) of batch image 0, {n} keypoints, {dt:.1f} s, "
+                     f"scaled by pixel count; "
+                     f"{'reference sources compiled copy-free (oracle/_ref)' if kind == 'reference' else 'oracle port'}"}
+    with S.SiftContext(1920, 1080, device=device) as c:
+        got = c.detect(crop)
+        stage = c.describe_given(want)      # the descriptor stage alone, on the reference's own keypoints
+    rec, prec, gi, wi = P.recall_precision(got, want)
+    rep = P.descriptor_report(got, want, gi, wi)
+    d = np.abs(got["desc"][gi].astype(np.int16) - want["desc"][wi].astype(np.int16)).max(1) if len(gi) else np.zeros(0)
+    g, w_ = got[gi][d > 1], want[wi][d > 1]
+    same = (g["x"] == w_["x"]) & (g["y"] == w_["y"]) & (g["size"] == w_["size"]) & (g["pori"] == w_["pori"])
+    parity = {"image": "1920x1080 crop of batch image 0 (this benchmark's generator), vs the reference run timed for cpu_baseline",
+              "keypoints_gpu": len(got), "keypoints_ref": len(want), "recall": rec, "precision": prec,
+              "pos_tol_px": P.POS_TOL, "size_rtol": P.SIZE_RTOL,
+              "desc_frac_within_1": rep["frac_le1"], "desc_frac_exact": rep["frac_exact"], "desc_max": rep["max"],
+              "n_outliers": int((d > 1).sum()), "outliers_with_identical_keypoint": int(same.sum()),
+              "desc_stage_max": int(np.abs(stage["desc"].astype(np.int16) - want["desc"].astype(np.int16)).max())}
+    return cpu, parity
 
 
 # ------------------------------------------------------------------------------------------
@@ -386,7 +407,7 @@ def run_b200(args):
                 t = marks_acc[idx] / reps
                 per_kernel.append({"kernel": name, "ms": t, "algorithmic_bytes": bpp * px0,
                                    "achieved": bpp * px0 / (t * 1e-3) / 1e9, "frac": bpp * px0 / (t * 1e-3) / 1e9 / hbm_peak})
-        roof = {"bound": "hbm", "kernel": "pyramid: fused cascade G0->G1..G3,D0..D2,next base + G3->D3,D4 (k_stream on octaves >= 20 Mpx, k_cascade below), all octaves of one image", "achieved": achieved,
+        roof = {"bound": "hbm", "kernel": "pyramid: fused cascade G0->G1..G3,D0..D2,next base + G3->D3,D4 (k_stream on octaves >= 2 Mpx, k_cascade below), all octaves of one image", "achieved": achieved,
                 "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                 "algorithmic_bytes": pyr_bytes, "ms": stages["pyramid"], "launches": nl["pyramid"],
                 "peak_source": peak_src, "per_kernel": per_kernel,
@@ -426,10 +447,33 @@ def run_b200(args):
                  "path": "tcgen05" if c0.match_path(nm, nm) else "simt", "data_in_l2": True,
                  "note": "2*N1*N2*128 / t; both descriptor sets (5 MB) are L2-resident by construction of the problem"}
 
-    cpu = None
+    # ---- single-image latency: one context, one image at a time, device-resident input, graph replay ----
+    latency = None
+    if rank == 0:
+        c0 = ctxs[0]
+        for k in range(3):
+            c0.detect_enqueue(d_imgs[k % len(d_imgs)], W, H)
+            c0.detect_finish()
+        reps = min(len(d_imgs), 16)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(streams[0])
+        for k in range(reps):
+            c0.detect_enqueue(d_imgs[k % len(d_imgs)], W, H)
+        e1.record(streams[0])
+        c0.detect_finish()
+        back_to_back = e0.elapsed_time(e1) / reps
+        t0 = time.perf_counter()
+        for k in range(reps):
+            c0.detect_enqueue(d_imgs[k % len(d_imgs)], W, H)
+            c0.detect_finish()
+        latency = {"ms_per_image_one_stream": back_to_back, "ms_enqueue_to_finish_host": 1e3 * (time.perf_counter() - t0) / reps,
+                   "how": "one context; CUDA events around 16 back-to-back detect calls / host clock around enqueue + finish",
+                   "graph": bool(int(os.environ.get("SIFT_B200_GRAPH", "1")))}
+
+    cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cpu = cpu_baseline_sample(h_imgs[0].numpy())
+            cpu, parity = cpu_baseline_sample(h_imgs[0].numpy(), local)
         except Exception as ex:  # the oracle is only a reported baseline; never fatal
             cpu = {"error": repr(ex)}
 
@@ -447,7 +491,8 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_step,
                     "d2h_bytes_per_step": d2h_step, "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "stages_ms": stages, "stage_launches": stage_launches, "match": match,
+            "stages_ms": stages, "stage_launches": stage_launches, "match": match, "latency": latency,
+            "parity": parity,
         }
         emit(line)
     for c in ctxs:

@@ -149,6 +149,59 @@ void* sift_b200_stream(sift_b200_ctx* ctx);
  * 0 = SIMT dp4a kernel (small problems). */
 int sift_b200_match_path(int na, int nb);
 
+/* ---- batch and multi-GPU --------------------------------------------------------------
+ * The reference drives one image pair from one thread (main.cpp:12-18).  A batch or a stitching collection repeats
+ * detect per image and match_keypoints per image pair; images are independent (no collective), matching needs one
+ * exchange step.  Everything below is driven by the host thread(s) of the caller: one process with several
+ * contexts (one per GPU, or several per GPU), or one process per GPU (MPI / torchrun style). */
+
+/* Batch detect: image k goes to ctxs[k % n_ctx] (contexts of one GPU = images in flight on it; contexts of
+ * different GPUs = the batch sharded by image, config 3).  images[k]: width x height x channels u8, HOST (pinned for
+ * asynchronous copies) or DEVICE memory of that context's GPU.  outs[k] / capacities[k] / counts[k]: as in
+ * sift_b200_detect_u8.  Returns the first non-OK status (all images are still attempted). */
+int sift_b200_detect_batch_u8(sift_b200_ctx* const* ctxs, int n_ctx, const uint8_t* const* images, int n_images,
+                              int width, int height, int channels, const sift_b200_params* params,
+                              sift_b200_keypoint* const* outs, const int32_t* capacities, int32_t* counts);
+
+/* NCCL communicator (libnccl.so.2 is loaded on first use).  One process per GPU: rank 0 calls comm_unique_id, ships
+ * the bytes to every rank by any means, and every rank calls comm_attach (collective).  One process driving several
+ * GPUs: comm_attach_all on its contexts (rank = position in the array).  world == 1 needs no NCCL. */
+#define SIFT_B200_UNIQUE_ID_BYTES 128
+int sift_b200_comm_unique_id(uint8_t* id_out /* SIFT_B200_UNIQUE_ID_BYTES */);
+int sift_b200_comm_attach(sift_b200_ctx* ctx, const uint8_t* id, int world, int rank);
+int sift_b200_comm_attach_all(sift_b200_ctx* const* ctxs, int n);
+int sift_b200_comm_info(const sift_b200_ctx* ctx, int* world, int* rank);
+
+/* Collection matching (config 5): match_keypoints (sift.cpp:783-815) for every unordered image pair i < j (and
+ * j -> i as well when both_directions), image i owned by rank i % world.  local_desc / local_counts: the n x 128 u8
+ * descriptor matrices (HOST or DEVICE) and row counts of the images THIS rank owns, in ascending image index.
+ * Collective: an all-reduce of the counts, then ONE ncclAllGather of the packed descriptor blocks on the context's
+ * side stream while the pairs whose images are both local already run; pairs are dealt to ranks by n_i * n_j
+ * weight (sift_b200_partition_pairs), never split.  Results (per row of image i: nearest row of image j and the two
+ * smallest squared distances) stay on the GPU; *n_pairs = pairs this rank owns.  Enqueued, not synchronised. */
+int sift_b200_collection_match(sift_b200_ctx* ctx, int n_images, const uint8_t* const* local_desc,
+                               const int32_t* local_counts, int both_directions, int* n_pairs);
+/* The same for one process driving every rank: desc[i] / counts[i] for ALL images, desc[i] reachable from the GPU
+ * of ctxs[i % n] (or HOST). */
+int sift_b200_collection_match_all(sift_b200_ctx* const* ctxs, int n, int n_images, const uint8_t* const* desc,
+                                   const int32_t* counts, int both_directions);
+/* The pairs this rank owns, in result order: (i, j, rows of image i). */
+int sift_b200_collection_pairs(sift_b200_ctx* ctx, int32_t* pair_i, int32_t* pair_j, int32_t* rows, int capacity,
+                               int* count);
+/* Matches of owned pair `pair` after the ratio test (HOST outputs, same contract as sift_b200_match). */
+int sift_b200_collection_fetch(sift_b200_ctx* ctx, int pair, double ratio, int32_t* idx_a, int32_t* idx_b,
+                               double* dist, int capacity, int* count);
+/* Device pointers to owned pair `pair`'s per-row results (valid until the next collection call). */
+int sift_b200_collection_device(sift_b200_ctx* ctx, int pair, const int32_t** d_best_idx, const int32_t** d_best_d2,
+                                const int32_t** d_second_d2, int* rows);
+/* Digest of this rank's results -- number of matches under `ratio` and an order-free 64-bit checksum over
+ * (pair, row, nearest index, d1^2, d2^2) -- summed over every rank when all_ranks (collective then): any number of
+ * GPUs must report the same two numbers for the same collection. */
+int sift_b200_collection_digest(sift_b200_ctx* ctx, double ratio, int all_ranks, int64_t* n_matches, uint64_t* hash);
+/* The deal itself (pure host code, no GPU): pairs of `rank` among `world`, longest-processing-time on n_i * n_j. */
+int sift_b200_partition_pairs(const int32_t* counts, int n_images, int world, int both_directions, int rank,
+                              int32_t* pair_i, int32_t* pair_j, int capacity, int* count);
+
 /* ---- introspection used by the parity tests (stage-by-stage comparison with the oracle) ---- */
 #define SIFT_B200_PLANE_GAUSSIAN 0 /* layer 0..5 */
 #define SIFT_B200_PLANE_DOG 1      /* layer 0..4 */

@@ -15,4 +15,9 @@ from .api import (  # noqa: F401
     library_path,
     load_library,
     declared_symbols,
+    comm_unique_id,
+    comm_attach_all,
+    collection_match_all,
+    partition_pairs_native,
+    detect_batch,
 )

@@ -98,6 +98,18 @@ def load_library():
         "sift_b200_debug_keypoints": (i32, [vp, i32, vp, i32, i32p]),
         "sift_b200_launch_count": (C.c_long, [vp]),
         "sift_b200_graphs_built": (C.c_long, [vp]),
+        "sift_b200_detect_batch_u8": (i32, [vp, i32, vp, i32, i32, i32, i32, PP, vp, vp, vp]),
+        "sift_b200_comm_unique_id": (i32, [vp]),
+        "sift_b200_comm_attach": (i32, [vp, vp, i32, i32]),
+        "sift_b200_comm_attach_all": (i32, [vp, i32]),
+        "sift_b200_comm_info": (i32, [vp, i32p, i32p]),
+        "sift_b200_collection_match": (i32, [vp, i32, vp, vp, i32, i32p]),
+        "sift_b200_collection_match_all": (i32, [vp, i32, i32, vp, vp, i32]),
+        "sift_b200_collection_pairs": (i32, [vp, vp, vp, vp, i32, i32p]),
+        "sift_b200_collection_fetch": (i32, [vp, i32, C.c_double, vp, vp, vp, i32, i32p]),
+        "sift_b200_collection_device": (i32, [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i32p]),
+        "sift_b200_collection_digest": (i32, [vp, C.c_double, i32, C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]),
+        "sift_b200_partition_pairs": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, i32p]),
         "sift_b200_debug_orient": (i32, [vp, vp, i32, vp, i32, i32p]),
         "sift_b200_debug_describe": (i32, [vp, vp, i32]),
         "sift_b200_debug_launch_plan": (i32, [vp, i32, i32, i32]),
@@ -274,6 +286,52 @@ class SiftContext:
     def match_path(self, na, nb):
         return self._L.sift_b200_match_path(na, nb)
 
+    # ---- multi-GPU: NCCL communicator + collection matching behind the C ABI ----
+    def comm_attach(self, unique_id, world, rank):
+        """Collective: every rank passes the bytes rank 0 got from comm_unique_id()."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id)) if unique_id is not None else None
+        self._check(self._L.sift_b200_comm_attach(self._h, buf, world, rank))
+
+    def comm_info(self):
+        w, r = C.c_int(1), C.c_int(0)
+        self._check(self._L.sift_b200_comm_info(self._h, C.byref(w), C.byref(r)))
+        return w.value, r.value
+
+    def collection_match(self, n_images, local_descs, both_directions=False):
+        """local_descs: the (n_i, 128) uint8 matrices (numpy / torch CUDA) of the images this rank owns
+        (image % world == rank), ascending image index.  Enqueues the exchange and every owned pair; returns the
+        number of owned pairs."""
+        keep = [np.ascontiguousarray(d, dtype=np.uint8) if isinstance(d, np.ndarray) else d.contiguous() for d in local_descs]
+        ptrs = (C.c_void_p * max(len(keep), 1))(*[(_ptr(d) if d.shape[0] else None) for d in keep])
+        counts = (C.c_int32 * max(len(keep), 1))(*[int(d.shape[0]) for d in keep])
+        n = C.c_int(0)
+        self._check(self._L.sift_b200_collection_match(self._h, n_images, ptrs, counts, int(both_directions), C.byref(n)))
+        self._coll_keep = keep   # host sources must outlive the asynchronous copies
+        return n.value
+
+    def collection_pairs(self):
+        n = C.c_int(0)
+        self._check(self._L.sift_b200_collection_pairs(self._h, None, None, None, 0, C.byref(n)))
+        pi, pj, rows = (np.zeros(max(n.value, 1), np.int32) for _ in range(3))
+        self._check(self._L.sift_b200_collection_pairs(self._h, pi.ctypes.data, pj.ctypes.data, rows.ctypes.data,
+                                                       n.value, C.byref(n)))
+        return pi[: n.value], pj[: n.value], rows[: n.value]
+
+    def collection_fetch(self, pair, rows, ratio_threshold=0.75):
+        cap = max(int(rows), 1)
+        ia, ib, d = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float64)
+        n = C.c_int(0)
+        self._check(self._L.sift_b200_collection_fetch(self._h, pair, float(ratio_threshold), ia.ctypes.data,
+                                                       ib.ctypes.data, d.ctypes.data, cap, C.byref(n)))
+        return ia[: n.value].copy(), ib[: n.value].copy(), d[: n.value].copy()
+
+    def collection_digest(self, ratio_threshold=0.75, all_ranks=True):
+        """(matches, checksum) of this rank's pairs, summed over all ranks when all_ranks (collective)."""
+        m, h = C.c_int64(0), C.c_uint64(0)
+        self._check(self._L.sift_b200_collection_digest(self._h, float(ratio_threshold), int(all_ranks),
+                                                        C.byref(m), C.byref(h)))
+        return m.value, h.value
+
     # ---- introspection for the parity tests ----
     def debug_options(self, keep_all_planes=False, unfused_pyramid=False):
         self._check(self._L.sift_b200_debug_options(self._h, int(keep_all_planes), int(unfused_pyramid)))
@@ -332,6 +390,76 @@ class SiftContext:
         out = np.zeros(max(n.value, 1), dtype=KP_DTYPE)
         self._check(self._L.sift_b200_debug_keypoints(self._h, stage, out.ctypes.data, n.value, C.byref(n)))
         return out[: n.value]
+
+
+def comm_unique_id():
+    """NCCL unique id (bytes) for SiftContext.comm_attach; call on rank 0 and ship to every rank."""
+    L = load_library()
+    buf = (C.c_uint8 * 128)()
+    rc = L.sift_b200_comm_unique_id(buf)
+    if rc:
+        raise SiftError(rc, L.sift_b200_last_error(None).decode())
+    return bytes(buf)
+
+
+def comm_attach_all(ctxs):
+    """One process driving several GPUs: contexts become ranks 0..n-1 of one communicator."""
+    L = load_library()
+    arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    rc = L.sift_b200_comm_attach_all(arr, len(ctxs))
+    if rc:
+        raise SiftError(rc, L.sift_b200_last_error(ctxs[0]._h).decode())
+
+
+def collection_match_all(ctxs, descs, both_directions=False):
+    """descs[i]: (n_i, 128) uint8 of image i, on the GPU of ctxs[i % n] or on the host."""
+    L = load_library()
+    arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    keep = [np.ascontiguousarray(d, dtype=np.uint8) if isinstance(d, np.ndarray) else d.contiguous() for d in descs]
+    ptrs = (C.c_void_p * max(len(keep), 1))(*[(_ptr(d) if d.shape[0] else None) for d in keep])
+    counts = (C.c_int32 * max(len(keep), 1))(*[int(d.shape[0]) for d in keep])
+    rc = L.sift_b200_collection_match_all(arr, len(ctxs), len(keep), ptrs, counts, int(both_directions))
+    if rc:
+        raise SiftError(rc, L.sift_b200_last_error(ctxs[0]._h).decode())
+    for c in ctxs:
+        c._coll_keep = keep
+
+
+def partition_pairs_native(counts, world, rank, both_directions=False):
+    """sift_b200_partition_pairs: the C++ deal of image pairs to ranks (pure host code)."""
+    L = load_library()
+    cnt = np.ascontiguousarray(counts, dtype=np.int32)
+    n = C.c_int(0)
+    L.sift_b200_partition_pairs(cnt.ctypes.data, len(cnt), world, int(both_directions), rank, None, None, 0, C.byref(n))
+    pi, pj = np.zeros(max(n.value, 1), np.int32), np.zeros(max(n.value, 1), np.int32)
+    rc = L.sift_b200_partition_pairs(cnt.ctypes.data, len(cnt), world, int(both_directions), rank, pi.ctypes.data,
+                                     pj.ctypes.data, n.value, C.byref(n))
+    if rc:
+        raise SiftError(rc, "partition_pairs")
+    return list(zip(pi[: n.value].tolist(), pj[: n.value].tolist()))
+
+
+def detect_batch(ctxs, images, capacity=None, **params):
+    """sift_b200_detect_batch_u8: image k on ctxs[k % len(ctxs)] (several contexts per GPU and / or several GPUs).
+    images: equally sized uint8 arrays (numpy host, ideally pinned, or torch CUDA tensors on the right GPU)."""
+    L = load_library()
+    p = make_params(**params)
+    n = len(images)
+    shape = tuple(images[0].shape)
+    h, w = shape[0], shape[1]
+    ch = 1 if len(shape) == 2 else shape[2]
+    keep = [np.ascontiguousarray(im) if isinstance(im, np.ndarray) else im.contiguous() for im in images]
+    cap = capacity if capacity is not None else max(4096, (w * h) // 16)
+    outs = [np.zeros(cap, dtype=KP_DTYPE) for _ in range(n)]
+    arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    img_p = (C.c_void_p * max(n, 1))(*[_ptr(k) for k in keep])
+    out_p = (C.c_void_p * max(n, 1))(*[o.ctypes.data for o in outs])
+    caps = (C.c_int32 * max(n, 1))(*([cap] * n))
+    counts = (C.c_int32 * max(n, 1))()
+    rc = L.sift_b200_detect_batch_u8(arr, len(ctxs), img_p, n, w, h, ch, C.byref(p), out_p, caps, counts)
+    if rc:
+        raise SiftError(rc, L.sift_b200_last_error(ctxs[0]._h).decode())
+    return [o[: counts[k]].copy() for k, o in enumerate(outs)]
 
 
 def detect_keypoints_and_descriptors(image, double_image_size=True, init_sigma=1.6, intervals=3,

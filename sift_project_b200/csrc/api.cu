@@ -26,7 +26,10 @@ using namespace sb;
 
 static thread_local std::string g_create_error;
 
+struct sift_b200_collection;
+
 struct sift_b200_ctx {
+    sift_b200_collection* coll = nullptr;   // communicator + collection-matching state (api_collection.inc)
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
@@ -96,6 +99,8 @@ struct sift_b200_ctx {
 };
 
 namespace {
+
+void collection_free(sift_b200_ctx* c);   // api_collection.inc
 
 int fail(sift_b200_ctx* c, int code, const char* fmt, ...) {
     char buf[512];
@@ -586,7 +591,7 @@ int sift_b200_create(int device, int max_width, int max_height, sift_b200_ctx** 
     }
     if (const char* m = getenv("SIFT_B200_CENTER")) c->centred = atoi(m) != 0;   // experiments
     if (const char* m = getenv("SIFT_B200_GRAPH")) c->use_graph = atoi(m) != 0;
-    if (const char* m = getenv("SIFT_B200_EXTREMA")) c->extrema_form = atoi(m) == 1 ? 1 : 0;
+    if (const char* m = getenv("SIFT_B200_EXTREMA")) c->extrema_form = atoi(m);
     c->max_w = max_width;
     c->max_h = max_height;
 #define CRT(call)                                                                                   \
@@ -646,6 +651,8 @@ void sift_b200_destroy(sift_b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->side) cudaStreamSynchronize(c->side);
+    collection_free(c);
     void* ptrs[] = {c->arena, c->d_input, c->d_pyr, c->d_counters, c->d_range, c->d_cands, c->d_raw, c->d_oriented,
                     c->d_records, c->d_desc, c->ss.bucket_cnt, c->ss.bucket_off, c->ss.bucket_fill,
                     c->ss.uniq_cnt, c->ss.uniq_off, c->ss.perm, c->ss.tmp_sorted, c->ss.sorted,
@@ -1034,7 +1041,7 @@ int sift_b200_debug_launch_plan(sift_b200_ctx* c, int use_graph, int centred, in
     if (!c) return SIFT_B200_E_INVALID;
     if (use_graph >= 0) c->use_graph = use_graph != 0;
     if (centred >= 0) c->centred = centred != 0;
-    if (extrema_form >= 0) c->extrema_form = extrema_form == 1 ? 1 : 0;
+    if (extrema_form >= 0) c->extrema_form = extrema_form;
     return SIFT_B200_OK;
 }
 
@@ -1043,3 +1050,5 @@ long sift_b200_graphs_built(const sift_b200_ctx* c) { return c ? c->graphs_built
 long sift_b200_launch_count(const sift_b200_ctx* c) { return c ? c->launches : 0; }
 
 }  // extern "C"
+
+#include "api_collection.inc"

@@ -183,11 +183,9 @@ k_extrema(const OctaveDesc oct, int octave, float thr, Cand* __restrict__ cands,
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 constexpr int EX4_STRIP = 124;   // tested columns per warp: 128 loaded minus 2 on each side (kept a multiple of 4)
-#ifndef SB_EX4_CTAS
-#define SB_EX4_CTAS 3
-#endif
-template <int ND>
-__global__ void __launch_bounds__(128, SB_EX4_CTAS)
+// SLOTS = rows of the rotating register window (3 in use + SLOTS - 3 in flight), CTAS = CTAs per SM
+template <int ND, int SLOTS, int CTAS>
+__global__ void __launch_bounds__(128, CTAS)
 k_extrema4(const OctaveDesc oct, int octave, float thr, int rows, Cand* __restrict__ cands, int cap,
            Counters* __restrict__ counters) {
     constexpr int NZ = ND - 2;
@@ -207,7 +205,7 @@ k_extrema4(const OctaveDesc oct, int octave, float thr, int rows, Cand* __restri
         const int pos = 4 * lane + c, x = x0 + c;
         if (pos >= 2 && pos <= EX4_STRIP + 1 && x >= 1 && x <= w - 2) ok |= 1u << c;
     }
-    float4 win[4][ND];
+    float4 win[SLOTS][ND];
     auto fetch = [&](int y, int slot) {
         const unsigned off = (unsigned)min(y, h - 1) * (unsigned)pitch + xl;   // a plane has < 2^31 pixels
 #pragma unroll
@@ -266,15 +264,16 @@ k_extrema4(const OctaveDesc oct, int octave, float thr, int rows, Cand* __restri
             }
         }
     };
-    fetch(ys - 1, 0); fetch(ys, 1); fetch(ys + 1, 2);
-#pragma unroll 1
-    for (int y0 = ys; y0 <= ye; y0 += 4) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {   // unrolled by the slot count: the window rotates without register moves
+    for (int j = 0; j < SLOTS - 1; ++j) fetch(ys - 1 + j, j);
+#pragma unroll 1
+    for (int y0 = ys; y0 <= ye; y0 += SLOTS) {
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j) {   // unrolled by the slot count: the window rotates without register moves
             const int y = y0 + j;
             if (y > ye) break;
-            fetch(y + 2, (j + 3) & 3);   // in flight while this row and the next are tested
-            test_row(win[j & 3], win[(j + 1) & 3], win[(j + 2) & 3], y);
+            fetch(y + SLOTS - 2, (j + SLOTS - 1) % SLOTS);   // in flight while this row and the next ones are tested
+            test_row(win[j % SLOTS], win[(j + 1) % SLOTS], win[(j + 2) % SLOTS], y);
         }
     }
 }
@@ -891,13 +890,21 @@ cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int bord
         // rows per warp: long walks on large octaves (2 halo rows each), short ones where the grid would not fill the GPU
         const int rows = px >= (16ll << 20) ? 32 : px >= (1ll << 20) ? 16 : px >= (1ll << 16) ? 4 : 2;
         dim3 grid(oct.w / EX4_STRIP + 1, (oct.h - 2 + 4 * rows - 1) / (4 * rows));
+#define SB_EX4(ND, SL, CT) k_extrema4<ND, SL, CT><<<grid, 128, 0, s>>>(oct, octave, (float)threshold, rows, cands, cap, counters)
         switch (dogs) {
-            case 4: k_extrema4<4><<<grid, 128, 0, s>>>(oct, octave, (float)threshold, rows, cands, cap, counters); break;
-            case 5: k_extrema4<5><<<grid, 128, 0, s>>>(oct, octave, (float)threshold, rows, cands, cap, counters); break;
-            case 6: k_extrema4<6><<<grid, 128, 0, s>>>(oct, octave, (float)threshold, rows, cands, cap, counters); break;
-            case 7: k_extrema4<7><<<grid, 128, 0, s>>>(oct, octave, (float)threshold, rows, cands, cap, counters); break;
+            case 4: SB_EX4(4, 4, 3); break;
+            case 5:
+                if (form == 2) SB_EX4(5, 4, 4);        // experiments: window depth / occupancy
+                else if (form == 3) SB_EX4(5, 5, 3);
+                else if (form == 4) SB_EX4(5, 6, 2);
+                else if (form == 5) SB_EX4(5, 5, 4);
+                else SB_EX4(5, 4, 3);
+                break;
+            case 6: SB_EX4(6, 4, 3); break;
+            case 7: SB_EX4(7, 4, 3); break;
             default: return cudaErrorInvalidValue;
         }
+#undef SB_EX4
         return cudaGetLastError();
     }
     // rows per warp: 32 on large octaves, 8 on mid-size ones, 2 on tiny ones (more warps, shorter serial walks)

@@ -27,6 +27,20 @@ def test_partition_covers_every_pair_once_and_balances():
     assert Cn.partition_pairs(counts, 4) == Cn.partition_pairs(counts, 4)  # deterministic
 
 
+def test_native_partition_equals_the_python_one():
+    """sift_b200_partition_pairs (C++, what sift_b200_collection_match uses) deals exactly like
+    collection.partition_pairs (pure host code: needs the built library, no GPU)."""
+    import sift_project_b200 as S
+    rng = np.random.default_rng(3)
+    for n, world, both in ((7, 2, False), (16, 8, False), (9, 3, True), (1, 2, False), (0, 1, False), (40, 4, False)):
+        counts = rng.integers(0, 5000, n).tolist()
+        if n > 3:
+            counts[2] = counts[1]          # equal costs: the tie-break must agree too
+        py = Cn.partition_pairs(counts, world, both)
+        for r in range(world):
+            assert S.partition_pairs_native(counts, world, r, both) == py[r], (n, world, r)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

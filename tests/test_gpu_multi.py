@@ -24,6 +24,46 @@ def test_collection_over_nccl():
     assert "collection ok" in out.stdout
 
 
+def test_collection_in_one_process_over_two_gpus():
+    """The reference's own caller is one C++ thread (main.cpp:12-18): sift_b200_comm_attach_all +
+    sift_b200_collection_match_all drive every GPU from one thread (grouped NCCL calls); batch detect deals the
+    images to the contexts.  Same digest as one GPU, every pair equal to the oracle."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    sys.path.insert(0, ROOT)
+    import sift_project_b200 as S
+    from oracle import oracle as O
+    imgs = [O.synth_image(240, 320, seed=70 + i) for i in range(5)]
+    ctxs = [S.SiftContext(320, 240, device=d) for d in (0, 1)]
+    kps = S.detect_batch(ctxs, imgs)
+    solo = [ctxs[0].detect(im) for im in imgs]
+    for a, b in zip(kps, solo):
+        assert a.tobytes() == b.tobytes()               # image k ran on GPU k % 2: same bytes as on GPU 0
+    descs = [np.ascontiguousarray(k["desc"]) for k in kps]
+    S.comm_attach_all(ctxs)
+    S.collection_match_all(ctxs, descs)
+    seen = {}
+    for c in ctxs:
+        pi, pj, rows = c.collection_pairs()
+        for q, (i, j, r) in enumerate(zip(pi, pj, rows)):
+            assert (int(i), int(j)) not in seen
+            seen[(int(i), int(j))] = c.collection_fetch(q, r)
+    assert sorted(seen) == [(i, j) for i in range(5) for j in range(i + 1, 5)]
+    for (i, j), (ia, ib, d) in seen.items():
+        wa, wb, wd = O.match(O.port(), descs[i], descs[j])
+        assert np.array_equal(ia, wa) and np.array_equal(ib, wb) and np.array_equal(d, wd), (i, j)
+    # per-rank digests (no collective from one thread) add up to the one-GPU digest
+    parts = [c.collection_digest(all_ranks=False) for c in ctxs]
+    one = S.SiftContext(64, 64, device=0)
+    one.collection_match(5, descs)
+    m, h = one.collection_digest(all_ranks=False)
+    assert m == sum(p[0] for p in parts) and h == sum(p[1] for p in parts) % (1 << 64)
+    for c in ctxs + [one]:
+        c.close()
+
+
 def test_drop_in_sift_binary(tmp_path):
     """the reference's main.cpp, unchanged, on top of sift_shim.cpp."""
     exe = os.path.join(ROOT, "oracle", "_ref", "sift_b200")

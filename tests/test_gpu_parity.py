@@ -21,7 +21,7 @@ REPORT = {}
 
 @pytest.fixture(scope="module")
 def ctx():
-    c = S.SiftContext(1024, 768)
+    c = S.SiftContext(1040, 768)
     yield c
     c.close()
 
@@ -637,6 +637,44 @@ def test_config4_8k_properties():
     assert out["x"].min() >= 0 and out["x"].max() < 7680 and out["y"].max() < 4320
     assert set(np.unique(out["layer"])) <= {1, 2, 3}
     assert (out["desc"].astype(np.float64) ** 2).sum(1).min() > 0   # no empty descriptors
+
+
+def test_collection_through_the_c_abi_on_one_gpu(ctx):
+    """sift_b200_collection_match with world = 1 (no NCCL): every unordered pair once, in both directions on
+    request, empty sets included; each pair's matches equal match_keypoints (sift.cpp:783-815) on that pair."""
+    sets = [O.synth_descriptors(n, seed=200 + k) for k, n in enumerate((700, 0, 1, 333, 1500, 2))]
+    sets[4][10] = sets[0][5]
+    for both in (False, True):
+        n_pairs = ctx.collection_match(len(sets), sets, both_directions=both)
+        pi, pj, rows = ctx.collection_pairs()
+        want = S.partition_pairs_native([len(s) for s in sets], 1, 0, both)
+        assert n_pairs == len(want) == (30 if both else 15)
+        assert sorted(zip(pi.tolist(), pj.tolist())) == sorted(want)
+        total = 0
+        for q, (i, j, r) in enumerate(zip(pi, pj, rows)):
+            assert r == len(sets[i])
+            ia, ib, d = ctx.collection_fetch(q, r)
+            wa, wb, wd = O.match(O.port(), sets[i], sets[j])
+            assert np.array_equal(ia, wa) and np.array_equal(ib, wb) and np.array_equal(d, wd), (i, j)
+            total += len(ia)
+        m, h = ctx.collection_digest(all_ranks=True)
+        assert m == total
+        assert ctx.collection_digest(all_ranks=False) == (m, h)      # deterministic
+
+
+def test_batch_detect_over_several_contexts(synth):
+    """sift_b200_detect_batch_u8: image k on context k % n; same bytes as one call per image."""
+    imgs = [synth["image"], O.synth_image(192, 256, seed=1), O.synth_image(192, 256, seed=2),
+            O.synth_image(192, 256, seed=3), O.synth_image(192, 256, seed=4)]
+    ctxs = [S.SiftContext(256, 192) for _ in range(3)]
+    got = S.detect_batch(ctxs, imgs)
+    for im, g in zip(imgs, got):
+        assert g.tobytes() == ctxs[0].detect(im).tobytes()
+    with pytest.raises(S.SiftError) as e:
+        S.detect_batch(ctxs, imgs, capacity=10)
+    assert e.value.code == 4
+    for c in ctxs:
+        c.close()
 
 
 def test_match_self_is_identity(ctx):
