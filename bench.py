@@ -165,26 +165,54 @@ def host_synth_crop(h, w, seed):
     return O.synth_image(h, w, seed=seed)
 
 
+# sample sizes of the reference arm: (height, width, seconds one core needs, measured with oracle/_ref on this pool's
+# hosts).  The reference is single-threaded (no <thread>, OpenMP or SIMD in src/), so "all the host threads it can
+# use" = one independent process per core, each on its own image.
+REF_SAMPLES = [(2160, 3840, 130.0), (1080, 1920, 24.0), (540, 960, 5.5)]
+
+
 def run_reference_arm(args):
-    """bench.py --impl reference: every host core runs the reference detect on its own
-    960x540 sample (1/16 of a 4K image's pixels, same generator); value is scaled by pixels."""
+    """bench.py --impl reference: every host core runs the reference's detect_keypoints_and_descriptors
+    (sift.cpp:712-776, compiled from the reference's sources) on its own generator-D image per step.  The sample is
+    the largest of 4K / 1080p / 960x540 that keeps the whole --steps/--warmup run within ~4 minutes; smaller
+    samples are scaled to 4K images/s by pixel count, which FLATTERS the CPU (4K costs 4.9x a 1080p image for 4x
+    the pixels) -- same_config is true only for the 4K sample.  The line also carries one 1080p
+    timing on one core, so the scaling cpu_baseline uses is visible in the same run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    sh, sw = 540, 960
+    try:
+        mem_gb = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") / 2 ** 30
+    except (ValueError, OSError):
+        mem_gb = 64.0
+    n_steps = args.warmup + args.steps
+    budget_s = 240.0
+    sh, sw, est = REF_SAMPLES[-1]
+    for h, w, t in REF_SAMPLES:
+        need_gb = cores * 4.5 * (h * w) / (H4K * W4K)      # the FP64 pyramid of a 4K image is ~4.3 GB
+        if t * n_steps <= budget_s and need_gb < 0.7 * mem_gb:
+            sh, sw, est = h, w, t
+            break
     frac = (sh * sw) / (H4K * W4K)
     imgs = [host_synth_crop(sh, sw, 1234 + i) for i in range(cores)]
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores, initializer=_cpu_worker_init) as pool:
         times = []
-        for step in range(args.warmup + args.steps):
+        for step in range(n_steps):
             t = time.perf_counter()
             res = pool.map(_cpu_detect, imgs, chunksize=1)
             dt = time.perf_counter() - t
             if step >= args.warmup:
                 times.append(dt)
+        one_1080p = None
+        if (sh, sw) != (1080, 1920):
+            n1, t1 = pool.apply(_cpu_detect, (host_synth_crop(1080, 1920, 1234),))
+            one_1080p = {"seconds_one_core": t1, "keypoints": n1,
+                         "images_per_s_4k_equiv_all_cores": cores * 0.25 / t1,
+                         "note": "one 1920x1080 image on one otherwise idle core, scaled by pixel count and by the core "
+                                 "count: the scaling cpu_baseline (1 core) uses"}
     total = sum(times)
     value = args.steps * cores * frac / total
     kind = cpu_kind()
@@ -193,15 +221,78 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "synthetic 3840x2160 (4K) batch of 256 images, detect+describe",
-                   "sample": f"{cores} x 960x540 generator-D images per step (1/16 of a 4K image each), scaled by pixel count",
-                   "keypoints_per_sample": float(np.mean([r[0] for r in res]))},
+                   "sample": f"{cores} x {sw}x{sh} generator-D images per step (one per core, {frac:.4f} of a 4K image each)"
+                             + ("" if frac == 1.0 else ", scaled to 4K images/s by pixel count (flatters the CPU: "
+                                                       "cost grows faster than pixels)"),
+                   "same_config": frac == 1.0,
+                   "keypoints_per_sample": float(np.mean([r[0] for r in res])),
+                   "seconds_per_sample_per_core": total / args.steps,
+                   "one_1080p": one_1080p, "host_memory_gb": mem_gb},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind,
-                         "sample": f"{cores} processes x one 960x540 image per step; reference "
+                         "sample": f"{cores} processes x one {sw}x{sh} image per step; reference "
                                    f"{'copy-free build of /root/reference/src (bit-identical output)' if kind == 'reference' else 'CPU port oracle/sift_oracle.cpp'}"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def config1_pair(device):
+    """BASELINE.json config 1 (stitching/image1.jpg + image2.jpg, stb-decoded pixels in tests/golden): this repo's
+    detect x2 + match through the host-buffer C ABI, beside the reference on the same pair on one core
+    (copy-free build, bit-identical output) and the recorded wall time of the reference AS SHIPPED
+    (profiles/r2_config1_asshipped.json: the unmodified ./sift needs minutes because it deep-copies whole octaves per
+    extremum, sift.cpp:346 -- too long to repeat inside every benchmark run)."""
+    import multiprocessing as mp
+    from PIL import Image
+    import sift_project_b200 as S
+    px = [np.asarray(Image.open(os.path.join(ROOT, "tests", "golden", n + ".png"))) for n in ("image1", "image2")]
+    with S.SiftContext(px[0].shape[1], px[0].shape[0], device=device) as c:
+        for _ in range(2):
+            t = time.perf_counter()
+            k = [c.detect(p) for p in px]
+            ia, ib, d = c.match(k[0]["desc"], k[1]["desc"])
+            gpu_s = time.perf_counter() - t
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(1, initializer=_cpu_worker_init) as pool:
+        res = [pool.apply(_cpu_detect, (p.astype(np.float64), True)) for p in px]
+        t = time.perf_counter()
+        m = pool.apply(_cpu_match, (res[0][2]["desc"], res[1][2]["desc"]))
+        cpu_match_s = time.perf_counter() - t
+    shipped = None
+    try:
+        shipped = json.load(open(os.path.join(ROOT, "profiles", "r2_config1_asshipped.json")))
+    except Exception:
+        pass
+    return {"workload": "stitching/image1.jpg + image2.jpg (755x499 RGB): detect x2 + match, host buffers in and out",
+            "gpu_ms": 1e3 * gpu_s, "keypoints": [len(x) for x in k], "matches": len(ia),
+            "cpu_copy_free_s": res[0][1] + res[1][1] + cpu_match_s, "cpu_keypoints": [res[0][0], res[1][0]],
+            "cpu_matches": m, "cpu_cores": 1, "reference_as_shipped": shipped}
+
+
+def _cpu_match(a, b):
+    O = _W["O"]
+    lib = O.ref() if _W["kind"] == "reference" else O.port()
+    return len(O.match(lib, a, b)[0])
+
+
+def _cpu_match_timed(n):
+    O = _W["O"]
+    lib = O.ref() if _W["kind"] == "reference" else O.port()
+    a, b = O.synth_descriptors(n, seed=1234), O.synth_descriptors(n, seed=1235)
+    t = time.perf_counter()
+    O.match(lib, a, b)
+    return time.perf_counter() - t
+
+
+def cpu_match_baseline(n=4000):
+    """The reference's match_keypoints loop (sift.cpp:789-812) on one core: GFLOP/s by the same 2*N1*N2*128 count."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(1, initializer=_cpu_worker_init) as pool:
+        dt = pool.apply(_cpu_match_timed, (n,))
+    return {"value": 2.0 * n * n * 128 / dt / 1e9, "unit": "GFLOP/s", "cores": 1, "kind": cpu_kind(),
+            "sample": f"{n} x {n} config-5 style descriptors, {dt:.2f} s"}
 
 
 def cpu_baseline_sample(img_u8_host, device):
@@ -470,12 +561,21 @@ def run_b200(args):
                    "how": "one context; CUDA events around 16 back-to-back detect calls / host clock around enqueue + finish",
                    "graph": bool(int(os.environ.get("SIFT_B200_GRAPH", "1")))}
 
-    cpu = parity = None
+    cpu = parity = config1 = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             cpu, parity = cpu_baseline_sample(h_imgs[0].numpy(), local)
         except Exception as ex:  # the oracle is only a reported baseline; never fatal
             cpu = {"error": repr(ex)}
+        try:
+            config1 = config1_pair(local)
+        except Exception as ex:
+            config1 = {"error": repr(ex)}
+        try:
+            if match is not None:
+                match["cpu_baseline"] = cpu_match_baseline()
+        except Exception as ex:
+            match["cpu_baseline"] = {"error": repr(ex)}
 
     if rank == 0:
         line = {
@@ -492,7 +592,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": d2h_step, "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "stages_ms": stages, "stage_launches": stage_launches, "match": match, "latency": latency,
-            "parity": parity,
+            "parity": parity, "config1": config1,
         }
         emit(line)
     for c in ctxs:

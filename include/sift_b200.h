@@ -111,6 +111,12 @@ int sift_b200_detect_f32(sift_b200_ctx* ctx, const float* pixels, int width, int
                          int channels, const sift_b200_params* params, sift_b200_keypoint* out,
                          int capacity, int* count);
 
+/* Page-locked host memory for inputs and outputs (cudaHostAlloc): copies from / to it are truly asynchronous and
+ * overlap the kernels of other contexts (image_io.cpp:20-35 decodes into pageable memory; a caller that wants the
+ * input copy off the critical path decodes or converts into one of these instead).  Usable from any context. */
+int sift_b200_host_alloc(size_t bytes, void** out);
+void sift_b200_host_free(void* p);
+
 /* Asynchronous variant: enqueue the whole pipeline on the context's stream and leave the
  * results on the GPU; no host synchronisation happens.  pixels may be DEVICE memory (used in
  * place) or HOST memory (copied with cudaMemcpyAsync first -- pin it for a truly asynchronous

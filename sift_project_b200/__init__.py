@@ -20,4 +20,5 @@ from .api import (  # noqa: F401
     collection_match_all,
     partition_pairs_native,
     detect_batch,
+    pinned_array,
 )

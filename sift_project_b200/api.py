@@ -98,6 +98,8 @@ def load_library():
         "sift_b200_debug_keypoints": (i32, [vp, i32, vp, i32, i32p]),
         "sift_b200_launch_count": (C.c_long, [vp]),
         "sift_b200_graphs_built": (C.c_long, [vp]),
+        "sift_b200_host_alloc": (i32, [C.c_size_t, C.POINTER(vp)]),
+        "sift_b200_host_free": (None, [vp]),
         "sift_b200_detect_batch_u8": (i32, [vp, i32, vp, i32, i32, i32, i32, PP, vp, vp, vp]),
         "sift_b200_comm_unique_id": (i32, [vp]),
         "sift_b200_comm_attach": (i32, [vp, vp, i32, i32]),
@@ -390,6 +392,21 @@ class SiftContext:
         out = np.zeros(max(n.value, 1), dtype=KP_DTYPE)
         self._check(self._L.sift_b200_debug_keypoints(self._h, stage, out.ctypes.data, n.value, C.byref(n)))
         return out[: n.value]
+
+
+def pinned_array(shape, dtype=np.uint8):
+    """numpy array in page-locked host memory (sift_b200_host_alloc), freed when the last view goes away."""
+    import weakref
+    L = load_library()
+    count = int(np.prod(shape))
+    n = max(count * np.dtype(dtype).itemsize, 1)
+    p = C.c_void_p()
+    rc = L.sift_b200_host_alloc(n, C.byref(p))
+    if rc:
+        raise SiftError(rc, L.sift_b200_last_error(None).decode())
+    buf = (C.c_uint8 * n).from_address(p.value)
+    weakref.finalize(buf, L.sift_b200_host_free, p.value)
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
 
 def comm_unique_id():

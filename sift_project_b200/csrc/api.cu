@@ -425,7 +425,7 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     float* scratch = o0.G[layers - 1];
     const float centre = c->centred ? c->centre_u8 : 0.f;
     if (sizeof(T) == 1 && input_fused_supported(channels, taps[0]) && !c->force_unfused) {
-        CU(c, launch_input_u8((const uint8_t*)d_pixels, width, height, o0.G[0], bw, bh, o0.pitch, doubled, taps[0], centre, s));
+        CU(c, launch_input_u8((const uint8_t*)d_pixels, width, height, channels, o0.G[0], bw, bh, o0.pitch, doubled, taps[0], centre, s));
         prof_mark(c, SIFT_B200_STAGE_INPUT, 1);
     } else {
         if (sizeof(T) == 1)
@@ -679,6 +679,22 @@ int sift_b200_detect_u8(sift_b200_ctx* c, const uint8_t* pixels, int width, int 
 int sift_b200_detect_f32(sift_b200_ctx* c, const float* pixels, int width, int height, int channels,
                          const sift_b200_params* params, sift_b200_keypoint* out, int capacity, int* count) {
     return detect_sync<float>(c, pixels, width, height, channels, params, out, capacity, count);
+}
+
+int sift_b200_host_alloc(size_t bytes, void** out) {
+    if (!out || bytes == 0) return SIFT_B200_E_INVALID;
+    *out = nullptr;
+    const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, SIFT_B200_E_CUDA, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return SIFT_B200_OK;
+}
+
+void sift_b200_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+    cudaGetLastError();
 }
 
 int sift_b200_detect_enqueue_u8(sift_b200_ctx* c, const uint8_t* pixels, int width, int height, int channels,

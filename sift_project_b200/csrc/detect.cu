@@ -184,7 +184,9 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 
 constexpr int EX4_STRIP = 124;   // tested columns per warp: 128 loaded minus 2 on each side (kept a multiple of 4)
 // SLOTS = rows of the rotating register window (3 in use + SLOTS - 3 in flight), CTAS = CTAs per SM
-template <int ND, int SLOTS, int CTAS>
+// XW = 1: the 4 warps of a CTA take consecutive row bands of one strip; XW = 4: they take 4 adjacent strips of one
+// row band and walk down side by side, so that a CTA reads ~2 KB contiguous per plane row (DRAM pages)
+template <int ND, int SLOTS, int CTAS, int XW>
 __global__ void __launch_bounds__(128, CTAS)
 k_extrema4(const OctaveDesc oct, int octave, float thr, int rows, Cand* __restrict__ cands, int cap,
            Counters* __restrict__ counters) {
@@ -192,8 +194,10 @@ k_extrema4(const OctaveDesc oct, int octave, float thr, int rows, Cand* __restri
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w = oct.w, h = oct.h, pitch = oct.pitch;
-    const int x0 = blockIdx.x * EX4_STRIP - 4 + 4 * lane;   // this lane's first column; the strip tests lane positions 2..125
-    const int ys = 1 + (blockIdx.y * 4 + warp) * rows;      // first tested row of this warp
+    const int strip = XW == 4 ? blockIdx.x * 4 + warp : blockIdx.x;
+    if (strip * EX4_STRIP - 2 > w - 2) return;          // (XW = 4) a strip beyond the last tested column
+    const int x0 = strip * EX4_STRIP - 4 + 4 * lane;    // this lane's first column; the strip tests lane positions 2..125
+    const int ys = 1 + (XW == 4 ? blockIdx.y : blockIdx.y * 4 + warp) * rows;      // first tested row of this warp
     if (ys > h - 2) return;
     const int ye = min(ys + rows - 1, h - 2);
     // lanes hanging over the left / right end of the row load a clamped (wrong, unused) position: their columns are
@@ -890,14 +894,16 @@ cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int bord
         // rows per warp: long walks on large octaves (2 halo rows each), short ones where the grid would not fill the GPU
         const int rows = px >= (16ll << 20) ? 32 : px >= (1ll << 20) ? 16 : px >= (1ll << 16) ? 4 : 2;
         dim3 grid(oct.w / EX4_STRIP + 1, (oct.h - 2 + 4 * rows - 1) / (4 * rows));
-#define SB_EX4(ND, SL, CT) k_extrema4<ND, SL, CT><<<grid, 128, 0, s>>>(oct, octave, (float)threshold, rows, cands, cap, counters)
+        const int strips = oct.w / EX4_STRIP + 1;
+        const dim3 grid_x((strips + 3) / 4, (oct.h - 2 + rows - 1) / rows);   // XW = 4: warps side by side
+#define SB_EX4(ND, SL, CT) k_extrema4<ND, SL, CT, 1><<<grid, 128, 0, s>>>(oct, octave, (float)threshold, rows, cands, cap, counters)
+#define SB_EX4X(ND, SL, CT) k_extrema4<ND, SL, CT, 4><<<grid_x, 128, 0, s>>>(oct, octave, (float)threshold, rows, cands, cap, counters)
         switch (dogs) {
             case 4: SB_EX4(4, 4, 3); break;
             case 5:
-                if (form == 2) SB_EX4(5, 4, 4);        // experiments: window depth / occupancy
-                else if (form == 3) SB_EX4(5, 5, 3);
-                else if (form == 4) SB_EX4(5, 6, 2);
-                else if (form == 5) SB_EX4(5, 5, 4);
+                if (form == 2) SB_EX4X(5, 4, 3);        // experiments: warp layout / occupancy
+                else if (form == 3) SB_EX4X(5, 4, 4);
+                else if (form == 4) SB_EX4X(5, 3, 4);
                 else SB_EX4(5, 4, 3);
                 break;
             case 6: SB_EX4(6, 4, 3); break;
@@ -905,6 +911,7 @@ cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int bord
             default: return cudaErrorInvalidValue;
         }
 #undef SB_EX4
+#undef SB_EX4X
         return cudaGetLastError();
     }
     // rows per warp: 32 on large octaves, 8 on mid-size ones, 2 on tiny ones (more warps, shorter serial walks)

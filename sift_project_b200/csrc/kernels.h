@@ -17,8 +17,8 @@ cudaError_t launch_blur(const float* in, float* out, float* dog, float* dec, int
                         int dec_w, int dec_h, int dec_pitch, const BlurTaps& taps, cudaStream_t s);
 
 bool input_fused_supported(int channels, const BlurTaps& taps);
-cudaError_t launch_input_u8(const uint8_t* src, int sw, int sh, float* dst, int w, int h, int pitch, int doubled,
-                            const BlurTaps& taps, float centre, cudaStream_t s);
+cudaError_t launch_input_u8(const uint8_t* src, int sw, int sh, int channels, float* dst, int w, int h, int pitch,
+                            int doubled, const BlurTaps& taps, float centre, cudaStream_t s);
 bool cascade_supported(const BlurTaps* taps);
 cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, float* dec, int dec_w, int dec_h,
                                 int dec_pitch, bool keep_all, int sm_count, int mode, int part, cudaStream_t s);

@@ -446,51 +446,64 @@ struct InputGeom {
     static constexpr size_t kSmem = (size_t)(W0 * H0 + TWI * H0) * sizeof(float);
 };
 
-// TWI x THI = output tile, NTI = threads, MINBI = CTAs per SM
-template <bool DOUBLED, int TWI, int THI, int NTI, int MINBI>
+// convert_to_grayscale (image.cpp:14-22): 0.2126 R + 0.7152 G + 0.0722 B in FP64, products and sums rounded one by
+// one like the reference's (no FMA contraction), so the gray value is the reference's own double.
+__device__ __forceinline__ double gray_bt709(double r, double g, double b) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(0.2126, r), __dmul_rn(0.7152, g)), __dmul_rn(0.0722, b));
+}
+
+// TWI x THI = output tile, NTI = threads, MINBI = CTAs per SM, CH = channels of the u8 input (1 gray, 3 RGB).
+// Gray pixels are integers: the 2x bilinear values are quarter-integers, exact in FP32.  RGB pixels go through the
+// FP64 gray value and the FP64 bilinear form of k_prepare (rounded to FP32 once, after the centre is subtracted), so
+// the fused and the unfused input paths give the same bytes.
+template <bool DOUBLED, int TWI, int THI, int NTI, int MINBI, int CH>
 __global__ void __launch_bounds__(NTI, MINBI)
 k_input_u8(const uint8_t* __restrict__ src, int sw, int sh, float* __restrict__ dst, int w, int h, int pitch,
            const BlurTaps taps, const float centre) {
     constexpr int IN_W0 = InputGeom<TWI, THI>::W0, IN_H0 = InputGeom<TWI, THI>::H0;
     constexpr int TW = TWI, TH = THI, CT = NTI;
+    using V = typename std::conditional<CH == 1, float, double>::type;
     extern __shared__ __align__(16) float smem[];
     float* sA = smem;
     float* sT = smem + IN_W0 * IN_H0;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
     const bool inside = tx0 - IN_R >= 0 && ty0 - IN_R >= 0 && tx0 + TW + IN_R <= w && ty0 + TH + IN_R <= h;
+    auto px = [&](int x, int y) -> V {   // gray level of source pixel (x, y)
+        if (CH == 1) return (V)__ldg(src + (size_t)y * sw + x);
+        const uint8_t* p = src + ((size_t)y * sw + x) * 3;
+        return (V)gray_bt709((double)__ldg(p), (double)__ldg(p + 1), (double)__ldg(p + 2));
+    };
+    const V c = (V)centre, half = (V)0.5;
     if (DOUBLED && inside) {
         // interior tiles: one source pixel neighbourhood -> a 2x2 block of the up-sampled tile
-        // (p, (p+q)/2; (p+t)/2, ((p+q)/2+(t+u)/2)/2 -- the same exact quarter-integers)
+        // (p, (p+q)/2; (p+t)/2, ((p+q)/2+(t+u)/2)/2 -- resize_inter_bilinear's values, image.cpp:64-86)
         const int sx0 = (tx0 - IN_R) >> 1, sy0 = (ty0 - IN_R) >> 1;   // tile origin is even
         for (int idx = threadIdx.x; idx < (IN_W0 / 2) * (IN_H0 / 2); idx += CT) {
             const int br = idx / (IN_W0 / 2), bc = idx - br * (IN_W0 / 2);
             const int x0 = sx0 + bc, y0 = sy0 + br;
             const int x1 = min(x0 + 1, sw - 1), y1 = min(y0 + 1, sh - 1);
-            // (pixel - centre: integers below 2^8, so the quarter-integer averages below stay exact)
-            const float p = __ldg(src + (size_t)y0 * sw + x0) - centre, q = __ldg(src + (size_t)y0 * sw + x1) - centre;
-            const float t = __ldg(src + (size_t)y1 * sw + x0) - centre, u = __ldg(src + (size_t)y1 * sw + x1) - centre;
-            const float top = p * 0.5f + q * 0.5f, bot = t * 0.5f + u * 0.5f;
-            *reinterpret_cast<float2*>(sA + (2 * br) * IN_W0 + 2 * bc) = make_float2(p, top);
+            const V p = px(x0, y0), q = px(x1, y0), t = px(x0, y1), u = px(x1, y1);
+            const V top = p * half + q * half, bot = t * half + u * half;
+            *reinterpret_cast<float2*>(sA + (2 * br) * IN_W0 + 2 * bc) = make_float2((float)(p - c), (float)(top - c));
             *reinterpret_cast<float2*>(sA + (2 * br + 1) * IN_W0 + 2 * bc) =
-                make_float2(p * 0.5f + t * 0.5f, top * 0.5f + bot * 0.5f);
+                make_float2((float)((p * half + t * half) - c), (float)((top * half + bot * half) - c));
         }
     } else
     for (int idx = threadIdx.x; idx < IN_W0 * IN_H0; idx += CT) {
-        const int r = idx / IN_W0, c = idx - r * IN_W0;
-        const int X = min(max(tx0 - IN_R + c, 0), w - 1), Y = min(max(ty0 - IN_R + r, 0), h - 1);
-        float v;
+        const int r = idx / IN_W0, cc = idx - r * IN_W0;
+        const int X = min(max(tx0 - IN_R + cc, 0), w - 1), Y = min(max(ty0 - IN_R + r, 0), h - 1);
+        V v;
         if (DOUBLED) {
             const int x0 = X >> 1, y0 = Y >> 1;
             const int x1 = min(x0 + 1, sw - 1), y1 = min(y0 + 1, sh - 1);
-            const float fx = (X & 1) ? 0.5f : 0.0f, fy = (Y & 1) ? 0.5f : 0.0f;
-            const float p = __ldg(src + (size_t)y0 * sw + x0) - centre, q = __ldg(src + (size_t)y0 * sw + x1) - centre;
-            const float t = __ldg(src + (size_t)y1 * sw + x0) - centre, u = __ldg(src + (size_t)y1 * sw + x1) - centre;
-            const float top = p * (1.f - fx) + q * fx, bot = t * (1.f - fx) + u * fx;
-            v = top * (1.f - fy) + bot * fy;
+            const V fx = (X & 1) ? half : (V)0, fy = (Y & 1) ? half : (V)0;
+            const V p = px(x0, y0), q = px(x1, y0), t = px(x0, y1), u = px(x1, y1);
+            const V top = p * ((V)1 - fx) + q * fx, bot = t * ((V)1 - fx) + u * fx;
+            v = top * ((V)1 - fy) + bot * fy;
         } else {
-            v = (float)__ldg(src + (size_t)Y * sw + X) - centre;
+            v = px(X, Y);
         }
-        sA[idx] = v;
+        sA[idx] = (float)(v - c);
     }
     __syncthreads();
     cascade_hpass<CT, IN_R, IN_W0, TW, IN_R>(sA, sT, IN_H0, taps);
@@ -520,7 +533,7 @@ __global__ void k_prepare(const T* __restrict__ src, int sw, int sh, int ch, flo
     auto gray = [&](int sx, int sy) -> double {
         const T* p = src + ((size_t)sy * sw + sx) * ch;
         if (ch == 1) return (double)p[0];
-        return 0.2126 * (double)p[0] + 0.7152 * (double)p[1] + 0.0722 * (double)p[2];
+        return gray_bt709((double)p[0], (double)p[1], (double)p[2]);
     };
     double v;
     if (!doubled) {
@@ -577,10 +590,11 @@ cudaError_t init_blur_r() {
 // Per-device one-time setup (opt-in to > 48 KB dynamic shared memory); called by context creation.
 cudaError_t pyramid_init() {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_input_u8<true, 128, 32, 512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+#define SB_IN_ATTR(D, CH)                                                                                       \
+    if ((e = cudaFuncSetAttribute(k_input_u8<D, 128, 32, 512, 3, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)InputGeom<128, 32>::kSmem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_input_u8<false, 128, 32, 512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)InputGeom<128, 32>::kSmem)) != cudaSuccess) return e;
+    SB_IN_ATTR(true, 1) SB_IN_ATTR(false, 1) SB_IN_ATTR(true, 3) SB_IN_ATTR(false, 3)
+#undef SB_IN_ATTR
 #define SB_CASC_ATTR(R1, R2, R3, TWP, THP, NTP, MINB)                                                       \
     if ((e = cudaFuncSetAttribute(k_cascade<R1, R2, R3, TWP, THP, NTP, MINB>,                             \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
@@ -615,18 +629,20 @@ cudaError_t launch_blur(const float* in, float* out, float* dog, float* dec, int
 #undef SB_CASE
 }
 
-// u8 gray input -> G[0][0] (up-sample + initial blur); taps.radius must be 4
-bool input_fused_supported(int channels, const BlurTaps& taps) { return channels == 1 && taps.radius == IN_R; }
+// u8 gray or RGB input -> G[0][0] (gray + up-sample + initial blur); taps.radius must be 4
+bool input_fused_supported(int channels, const BlurTaps& taps) {
+    return (channels == 1 || channels == 3) && taps.radius == IN_R;
+}
 
-cudaError_t launch_input_u8(const uint8_t* src, int sw, int sh, float* dst, int w, int h, int pitch, int doubled,
-                            const BlurTaps& taps, float centre, cudaStream_t s) {
+cudaError_t launch_input_u8(const uint8_t* src, int sw, int sh, int channels, float* dst, int w, int h, int pitch,
+                            int doubled, const BlurTaps& taps, float centre, cudaStream_t s) {
     // tile shapes measured at 4K (ms): 128x64 / 512 threads / 2 per SM 0.088, 128x32 / 256 / 4 0.079,
     // 128x32 / 512 / 3 0.077, 64x64 / 256 / 4 0.077, 128x16 / 256 / 6 0.078
     dim3 grid((w + 127) / 128, (h + 31) / 32);
-    if (doubled)
-        k_input_u8<true, 128, 32, 512, 3><<<grid, 512, InputGeom<128, 32>::kSmem, s>>>(src, sw, sh, dst, w, h, pitch, taps, centre);
-    else
-        k_input_u8<false, 128, 32, 512, 3><<<grid, 512, InputGeom<128, 32>::kSmem, s>>>(src, sw, sh, dst, w, h, pitch, taps, centre);
+#define SB_IN(D, CH) k_input_u8<D, 128, 32, 512, 3, CH><<<grid, 512, InputGeom<128, 32>::kSmem, s>>>(src, sw, sh, dst, w, h, pitch, taps, centre)
+    if (channels == 3) { if (doubled) SB_IN(true, 3); else SB_IN(false, 3); }
+    else { if (doubled) SB_IN(true, 1); else SB_IN(false, 1); }
+#undef SB_IN
     return cudaGetLastError();
 }
 

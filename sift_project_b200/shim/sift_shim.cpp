@@ -68,6 +68,24 @@ sift_b200_ctx* context_for(int w, int h) {
     return ctx.get();
 }
 
+// Page-locked staging buffer for the pixels (grown on demand, one per host thread): the host -> device copy of
+// sift_b200_detect_* is then a true asynchronous DMA instead of a staged copy out of pageable memory.
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~PinnedBuf() { sift_b200_host_free(p); }
+    void* get(size_t bytes) {
+        if (bytes > cap) {
+            sift_b200_host_free(p);
+            p = nullptr; cap = 0;
+            if (sift_b200_host_alloc(bytes, &p) != SIFT_B200_OK)
+                throw std::runtime_error(std::string("sift_b200_host_alloc: ") + sift_b200_last_error(nullptr));
+            cap = bytes;
+        }
+        return p;
+    }
+};
+
 [[noreturn]] void fail(sift_b200_ctx* c, const char* what) {
     throw std::runtime_error(std::string(what) + ": " + sift_b200_last_error(c));
 }
@@ -107,17 +125,21 @@ std::vector<Keypoint> detect_keypoints_and_descriptors(const Image& img, const b
     }
     std::vector<Keypoint> out(std::max<size_t>(4096, (size_t)img.width * img.height / 16));
     int count = 0, rc;
+    thread_local PinnedBuf staging;
+    if (bytes_ok) {
+        uint8_t* px = static_cast<uint8_t*>(staging.get(n));
+        for (size_t i = 0; i < n; ++i) px[i] = (uint8_t)img.data[i];
+    } else {
+        float* px = static_cast<float*>(staging.get(n * sizeof(float)));
+        for (size_t i = 0; i < n; ++i) px[i] = (float)img.data[i];
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
-        if (bytes_ok) {
-            std::vector<uint8_t> px(n);
-            for (size_t i = 0; i < n; ++i) px[i] = (uint8_t)img.data[i];
-            rc = sift_b200_detect_u8(ctx, px.data(), img.width, img.height, img.channels, &p,
+        if (bytes_ok)
+            rc = sift_b200_detect_u8(ctx, static_cast<const uint8_t*>(staging.p), img.width, img.height, img.channels, &p,
                                      reinterpret_cast<sift_b200_keypoint*>(out.data()), (int)out.size(), &count);
-        } else {
-            std::vector<float> px(img.data.begin(), img.data.end());
-            rc = sift_b200_detect_f32(ctx, px.data(), img.width, img.height, img.channels, &p,
+        else
+            rc = sift_b200_detect_f32(ctx, static_cast<const float*>(staging.p), img.width, img.height, img.channels, &p,
                                       reinterpret_cast<sift_b200_keypoint*>(out.data()), (int)out.size(), &count);
-        }
         if (rc == SIFT_B200_E_CAPACITY && count > (int)out.size()) {
             out.resize(count);
             continue;

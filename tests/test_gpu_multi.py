@@ -77,6 +77,23 @@ def test_drop_in_sift_binary(tmp_path):
     assert finals == [1286, 1430]          # SURVEY.md section 4 known answers
     assert (tmp_path / "matches.png").stat().st_size > 10000
     assert (tmp_path / "keypoints.png").stat().st_size > 10000
+    # Pixel-diff against the PNGs the reference ITSELF writes (sift.cpp:765-768 keypoints.png of the last detect
+    # call, :850-876 matches.png), produced by oracle/_ref/sift as shipped on the same two images and stored as the
+    # overlay on top of the input pixels (tests/golden/make_golden_drawings.py).
+    import numpy as np
+    from PIL import Image
+    ref = np.load(os.path.join(g, "ref_drawings.npz"))
+    i1 = np.asarray(Image.open(os.path.join(g, "image1.png")))
+    i2 = np.asarray(Image.open(os.path.join(g, "image2.png")))
+    for name, base, key in (("keypoints.png", i2, "kp"), ("matches.png", np.concatenate([i1, i2], 1), "mt")):
+        want = base.copy().reshape(-1, 3)
+        want[ref[key + "_idx"]] = ref[key + "_rgb"]
+        want = want.reshape(tuple(ref[key + "_shape"]))
+        got = np.asarray(Image.open(tmp_path / name))
+        assert got.shape == want.shape, name
+        differing = float(np.any(got != want, -1).mean())
+        print(f"{name}: {differing:.6f} of the pixels differ from the reference's drawing")
+        assert differing < 2e-3, (name, differing)       # a ring or spoke end that rounds to the next pixel
 
 
 def test_collection_driver_on_a_synthetic_dataset(tmp_path):

@@ -759,6 +759,26 @@ def test_random_shapes_fused_equals_per_level(ctx):
     ctx.debug_options()
 
 
+def test_rgb_input_fused_equals_unfused(ctx):
+    """convert_to_grayscale + resize_inter_bilinear + the initial blur (image.cpp:8-24, 62-88, sift.cpp:113-126) for
+    RGB input: the fused input kernel (gray in FP64 exactly as the reference forms it, tile formed in shared memory)
+    and the unfused k_prepare + k_blur path give the same bytes, doubled or not, edges included."""
+    rng = np.random.default_rng(12)
+    for h, w in ((97, 131), (192, 256), (300, 413)):
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        g = O.synth_image(h, w, seed=h)
+        rgb = np.clip(rgb.astype(np.int32) // 8 + g[..., None].astype(np.int32) - 16, 0, 255).astype(np.uint8)
+        for doubled in (True, False):
+            ctx.debug_options(unfused_pyramid=1)
+            ref = ctx.detect(rgb, double_image_size=doubled)
+            base_ref = ctx.gaussian(0, 0)
+            ctx.debug_options(unfused_pyramid=0)
+            got = ctx.detect(rgb, double_image_size=doubled)
+            assert np.array_equal(ctx.gaussian(0, 0), base_ref), (h, w, doubled)
+            assert got.tobytes() == ref.tobytes() and len(got) > 20, (h, w, doubled)
+    ctx.debug_options()
+
+
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_random_small_images_vs_oracle(ctx, seed):
     rng = np.random.default_rng(seed)
