@@ -508,15 +508,8 @@ def run_b200(args):
     # ---- the matcher (the only tensor-core stage): one 20k x 20k pair of config 5, device-resident ----
     match = None
     if rank == 0:
-        def synth_desc(n, seed):
-            g = torch.Generator(device=dev); g.manual_seed(seed)
-            hh = torch.randn((n, 128), generator=g, device=dev).abs()
-            hh = hh / hh.norm(dim=1, keepdim=True)
-            hh = hh.clamp(max=0.2)
-            hh = hh / hh.norm(dim=1, keepdim=True)
-            return torch.floor(512.0 * hh).clamp(max=255).to(torch.uint8).contiguous()
         nm = 20000
-        da, db = synth_desc(nm, 1234), synth_desc(nm, 1235)
+        da, db = synth_desc_gpu(nm, 1234, dev), synth_desc_gpu(nm, 1235, dev)
         mi = torch.empty(nm, dtype=torch.int32, device=dev); m1 = torch.empty_like(mi); m2 = torch.empty_like(mi)
         torch.cuda.synchronize()
         c0 = ctxs[0]
@@ -561,6 +554,26 @@ def run_b200(args):
                    "how": "one context; CUDA events around 16 back-to-back detect calls / host clock around enqueue + finish",
                    "graph": bool(int(os.environ.get("SIFT_B200_GRAPH", "1")))}
 
+    # ---- config 5 in miniature on every run (and at every N of the scaling run): all-pairs matching of 32 x 8000
+    # descriptors through sift_b200_collection_match; at N > 1 the descriptors cross NVLink in one ncclAllGather
+    # issued by the library, and the all-reduced digest must equal the digest of one context doing it all ----
+    collection = None
+    try:
+        attach_comm(ctxs[0], rank, world)
+        c_sets, c_per = 32, 8000
+        ms_c, n_pairs_c, matches_c, digest_c, solo_c = collection_pass(ctxs[0], streams[0], c_sets, c_per, rank, world,
+                                                                       dev, steps=3, warmup=1, check_solo=True)
+        ms_c = reduce_max(ms_c)
+        if rank == 0:
+            flop = 2.0 * (c_sets * (c_sets - 1) // 2) * c_per * c_per * 128
+            collection = {"workload": f"{c_sets} sets x {c_per} descriptors, all {c_sets * (c_sets - 1) // 2} pairs, through "
+                                      "sift_b200_collection_match (NCCL all-gather inside the library at N > 1)",
+                          "ms": ms_c, "tflops_equivalent": flop / (ms_c * 1e-3) / 1e12, "pairs_on_rank0": n_pairs_c,
+                          "matches": matches_c, "digest": f"{digest_c:016x}",
+                          "one_gpu_digest": f"{solo_c[1]:016x}", "equals_one_gpu_run": (matches_c, digest_c) == tuple(solo_c)}
+    except Exception as ex:
+        collection = {"error": repr(ex)}
+
     cpu = parity = config1 = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -592,7 +605,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": d2h_step, "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "stages_ms": stages, "stage_launches": stage_launches, "match": match, "latency": latency,
-            "parity": parity, "config1": config1,
+            "parity": parity, "config1": config1, "collection": collection,
         }
         emit(line)
     for c in ctxs:
@@ -601,14 +614,65 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def synth_desc_gpu(n, seed, dev):
+    """Config-5 style descriptors on the GPU: |N(0,1)| through the reference's normalise -> clamp 0.2 ->
+    renormalise -> floor(512 x) -> min 255 (sift.cpp:582-602)."""
+    import torch
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    hh = torch.randn((n, 128), generator=g, device=dev).abs()
+    hh = hh / hh.norm(dim=1, keepdim=True)
+    hh = hh.clamp(max=0.2)
+    hh = hh / hh.norm(dim=1, keepdim=True)
+    return torch.floor(512.0 * hh).clamp(max=255).to(torch.uint8).contiguous()
+
+
+def attach_comm(ctx, rank, world):
+    """NCCL communicator inside libsift_b200.so: rank 0's unique id travels over torch.distributed (plumbing)."""
+    import torch.distributed as dist
+    import sift_project_b200 as S
+    if world == 1:
+        ctx.comm_attach(None, 1, 0)
+        return
+    uid = [S.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.comm_attach(uid[0], world, rank)
+
+
+def collection_pass(ctx, stream, n_sets, per, rank, world, dev, steps=2, warmup=1, check_solo=False):
+    """All-pairs matching of `n_sets` x `per` descriptors through the C ABI (sift_b200_collection_match: counts
+    all-reduce + ONE ncclAllGather on the side stream overlapped with the local pairs + every owned pair's top-2 on
+    tcgen05).  Returns (ms per pass -- CUDA events on the context's stream --, matches, digest, solo digest)."""
+    import torch
+    import sift_project_b200 as S
+    owned = [synth_desc_gpu(per, 1234 + i, dev) for i in range(n_sets) if i % world == rank]
+    torch.cuda.synchronize()
+    for _ in range(warmup):
+        ctx.collection_match(n_sets, owned)
+    ctx.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        n_pairs = ctx.collection_match(n_sets, owned)
+    e1.record(stream)
+    ctx.sync()
+    ms = e0.elapsed_time(e1) / steps
+    matches, digest = ctx.collection_digest(0.75, all_ranks=True)
+    solo = None
+    if check_solo and rank == 0:      # the whole collection on ONE context: same digest or the exchange is wrong
+        everything = [synth_desc_gpu(per, 1234 + i, dev) for i in range(n_sets)]
+        with S.SiftContext(64, 64, device=dev.index) as one:
+            one.collection_match(n_sets, everything)
+            solo = one.collection_digest(0.75, all_ranks=False)
+    return ms, n_pairs, matches, digest, solo
+
+
 def run_collection(args):
-    """BASELINE.json config 5: `--sets` descriptor sets x `--per-set` descriptors, all-pairs matching
-    partitioned over the ranks by image pair, after ONE NCCL all-gather of the u8 descriptor blocks.
-    Timed region (CUDA events + barrier, max over ranks): all-gather + every pair's top-2 search."""
+    """BASELINE.json config 5: `--sets` descriptor sets x `--per-set` descriptors, all-pairs matching partitioned
+    over the ranks by image pair, after ONE NCCL all-gather of the u8 descriptor blocks -- all inside the C ABI.
+    Timed region (CUDA events, max over ranks): all-gather + every pair's top-2 search."""
     import torch
     import torch.distributed as dist
     import sift_project_b200 as S
-    from sift_project_b200 import collection as Cn
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -621,50 +685,19 @@ def run_collection(args):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     n_sets, per = args.sets, args.per_set
-
-    def synth_desc(n, seed):
-        g = torch.Generator(device=dev); g.manual_seed(seed)
-        hh = torch.randn((n, 128), generator=g, device=dev).abs()
-        hh = hh / hh.norm(dim=1, keepdim=True)
-        hh = hh.clamp(max=0.2)
-        hh = hh / hh.norm(dim=1, keepdim=True)
-        return torch.floor(512.0 * hh).clamp(max=255).to(torch.uint8).contiguous()
-
-    local_sets = {i: synth_desc(per, 1234 + i) for i in range(n_sets) if Cn.owner_of(i, world) == rank}
     ctx = S.SiftContext(64, 64, device=local)
+    attach_comm(ctx, rank, world)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    main_s = torch.cuda.current_stream()
-    pairs = Cn.partition_pairs([per] * n_sets, world)[rank]
-    idx = torch.empty((len(pairs), per), dtype=torch.int32, device=dev)
-    d1, d2 = torch.empty_like(idx), torch.empty_like(idx)
-    torch.cuda.synchronize()
-
-    def one_pass():
-        descs, _ = Cn.all_gather_descriptors(local_sets, n_sets, device=dev)   # NCCL, torch's stream
-        e = torch.cuda.Event(); e.record(main_s); stream.wait_event(e)
-        for k, (i, j) in enumerate(pairs):
-            ctx.match_enqueue(descs[i], per, descs[j], per, idx[k], d1[k], d2[k])
-        e2 = torch.cuda.Event(); e2.record(stream); main_s.wait_event(e2)
-
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        one_pass()
-    torch.cuda.synchronize()
     if world > 1:
         dist.barrier(device_ids=[local])
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record(main_s)
-    for _ in range(args.steps):
-        one_pass()
-    t1.record(main_s)
-    torch.cuda.synchronize()
-    ms = torch.tensor([t0.elapsed_time(t1) / args.steps], dtype=torch.float64, device=dev)
-    matches = ((16 * d1.long() * d1.long()) < (9 * d2.long() * d2.long())).sum().to(torch.float64).reshape(1)
+    ms_local, n_pairs, matches, digest, _ = collection_pass(ctx, stream, n_sets, per, rank, world, dev,
+                                                            steps=args.steps, warmup=min(args.warmup, 1))
+    ms = torch.tensor([ms_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(matches, op=dist.ReduceOp.SUM)
     if rank == 0:
-        n_pairs = n_sets * (n_sets - 1) // 2
-        flop = 2.0 * n_pairs * per * per * 128
+        total_pairs = n_sets * (n_sets - 1) // 2
+        flop = 2.0 * total_pairs * per * per * 128
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -676,12 +709,12 @@ def run_collection(args):
             "metric": "collection all-pairs match (top-2 + ratio test)", "value": tf, "unit": "TFLOP/s-equivalent",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms.item()),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{n_sets} sets x {per} descriptors, {n_pairs} unordered pairs, "
-                                   f"all-gather of {n_sets * per * 128 / 1e9:.2f} GB + tile-partitioned matching",
-                       "pairs_on_rank0": len(pairs)},
+            "config": {"workload": f"{n_sets} sets x {per} descriptors, {total_pairs} unordered pairs, "
+                                   f"ncclAllGather of {n_sets * per * 128 / 1e9:.2f} GB inside libsift_b200.so + "
+                                   f"pair-partitioned matching", "pairs_on_rank0": n_pairs},
             "roofline": {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
                          "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained x n_gpus"},
-            "matches": float(matches.item())}))
+            "matches": matches, "digest": f"{digest:016x}"}))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -73,8 +73,10 @@ struct sift_b200_ctx {
     // extrema scan of each octave on a side stream, so the small octaves overlap the large ones ----
     bool use_graph = true;
     int extrema_form = 0;        // 0 = four columns per lane (default), 1 = one column per lane
-    cudaStream_t side = nullptr;
-    std::vector<cudaEvent_t> fork_ev;   // [0 .. kMaxOctaves): "octave chain reached o"; last: join
+    cudaStream_t side = nullptr, side2 = nullptr;
+    std::vector<cudaEvent_t> fork_ev;   // [0 .. kMaxOctaves): "octave chain reached o"; [kMaxOctaves]: join of the
+                                        // cascade branch; then [kMaxOctaves + 1 + o]: "D3, D4 of octave o written";
+                                        // last: join of the extrema branch
     cudaGraphExec_t graph_exec = nullptr;
     std::vector<uint8_t> graph_key;
     int graph_launches = 0;
@@ -269,8 +271,9 @@ struct DetectPlan {
 
 int enqueue_body(sift_b200_ctx* c, const DetectPlan& pl, bool forked, int* n_launches, int* stage_launches) {
     const StageParams& sp = c->sp;
-    cudaStream_t s = c->stream, s2 = forked ? c->side : c->stream;
+    cudaStream_t s = c->stream, s2 = forked ? c->side : c->stream, s3 = forked ? c->side2 : c->stream;
     int total = 0;
+    bool s3_forked = false;
     auto mark = [&](int stage, int launches) {
         total += launches;
         if (stage_launches) stage_launches[stage] += launches;
@@ -306,13 +309,22 @@ int enqueue_body(sift_b200_ctx* c, const DetectPlan& pl, bool forked, int* n_lau
             mark(SIFT_B200_STAGE_PYRAMID, pl.layers - 1);
         }
         if (od.w >= 2 * sp.border + 1 && od.h >= 2 * sp.border + 1) {
-            CU(c, launch_extrema(od, o, pl.dogs, sp.border, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, c->extrema_form, s2));
+            if (forked) {   // the extrema scans form a third branch: octave o's scan only waits for octave o's planes
+                CU(c, cudaEventRecord(c->fork_ev[kMaxOctaves + 1 + o], s2));
+                CU(c, cudaStreamWaitEvent(s3, c->fork_ev[kMaxOctaves + 1 + o], 0));
+                s3_forked = true;
+            }
+            CU(c, launch_extrema(od, o, pl.dogs, sp.border, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, c->extrema_form, s3));
             mark(SIFT_B200_STAGE_EXTREMA, 1);
         }
     }
     if (forked) {
         CU(c, cudaEventRecord(c->fork_ev[kMaxOctaves], s2));
         CU(c, cudaStreamWaitEvent(s, c->fork_ev[kMaxOctaves], 0));
+        if (s3_forked) {
+            CU(c, cudaEventRecord(c->fork_ev[2 * kMaxOctaves + 1], s3));
+            CU(c, cudaStreamWaitEvent(s, c->fork_ev[2 * kMaxOctaves + 1], 0));
+        }
     }
     CU(c, launch_refine(c->d_pyr, c->d_cands, c->d_raw, c->d_counters, sp, c->sm_count, s));
     mark(SIFT_B200_STAGE_REFINE, 1);
@@ -606,7 +618,8 @@ int sift_b200_create(int device, int max_width, int max_height, sift_b200_ctx** 
     CRT(cudaSetDevice(device));
     CRT(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CRT(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
-    for (int i = 0; i <= kMaxOctaves; ++i) {
+    CRT(cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking));
+    for (int i = 0; i <= 2 * kMaxOctaves + 1; ++i) {
         cudaEvent_t e;
         CRT(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         c->fork_ev.push_back(e);
@@ -666,6 +679,7 @@ void sift_b200_destroy(sift_b200_ctx* c) {
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->side) cudaStreamDestroy(c->side);
+    if (c->side2) cudaStreamDestroy(c->side2);
     if (c->stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
     delete c;

@@ -22,6 +22,7 @@ def test_collection_over_nccl():
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "collection ok" in out.stdout
+    print([l for l in out.stdout.splitlines() if "collection ok" in l][0])
 
 
 def test_collection_in_one_process_over_two_gpus():
