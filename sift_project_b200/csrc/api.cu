@@ -72,6 +72,7 @@ struct sift_b200_ctx {
     // chain (first cascade kernel of every octave) runs on the main stream and the second cascade kernel + the
     // extrema scan of each octave on a side stream, so the small octaves overlap the large ones ----
     bool use_graph = true;
+    bool three_branches = false; // experiments (SIFT_B200_GRAPH=3): extrema scans on a third graph branch
     int extrema_form = 0;        // 0 = four columns per lane (default), 1 = one column per lane
     cudaStream_t side = nullptr, side2 = nullptr;
     std::vector<cudaEvent_t> fork_ev;   // [0 .. kMaxOctaves): "octave chain reached o"; [kMaxOctaves]: join of the
@@ -271,7 +272,10 @@ struct DetectPlan {
 
 int enqueue_body(sift_b200_ctx* c, const DetectPlan& pl, bool forked, int* n_launches, int* stage_launches) {
     const StageParams& sp = c->sp;
-    cudaStream_t s = c->stream, s2 = forked ? c->side : c->stream, s3 = forked ? c->side2 : c->stream;
+    // (a third branch for the extrema scans was measured and dropped: 4K latency 1.64 ms against 1.60 ms with two
+    // branches, batch throughput -4 %: the scans then compete with the next octave's cascade kernels for the SMs)
+    const bool three = forked && c->three_branches;
+    cudaStream_t s = c->stream, s2 = forked ? c->side : c->stream, s3 = three ? c->side2 : s2;
     int total = 0;
     bool s3_forked = false;
     auto mark = [&](int stage, int launches) {
@@ -309,7 +313,7 @@ int enqueue_body(sift_b200_ctx* c, const DetectPlan& pl, bool forked, int* n_lau
             mark(SIFT_B200_STAGE_PYRAMID, pl.layers - 1);
         }
         if (od.w >= 2 * sp.border + 1 && od.h >= 2 * sp.border + 1) {
-            if (forked) {   // the extrema scans form a third branch: octave o's scan only waits for octave o's planes
+            if (three) {   // the extrema scans form a third branch: octave o's scan only waits for octave o's planes
                 CU(c, cudaEventRecord(c->fork_ev[kMaxOctaves + 1 + o], s2));
                 CU(c, cudaStreamWaitEvent(s3, c->fork_ev[kMaxOctaves + 1 + o], 0));
                 s3_forked = true;
@@ -463,7 +467,7 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     std::vector<uint8_t> key;
     auto put = [&](const void* q, size_t n) { key.insert(key.end(), (const uint8_t*)q, (const uint8_t*)q + n); };
     put(&pl, sizeof pl); put(&sp, sizeof sp); put(&c->pyr, sizeof c->pyr); put(&c->ss.nb, sizeof(int));
-    const int dbg[4] = {c->keep_planes, c->force_unfused, c->fused_mode, c->extrema_form};
+    const int dbg[5] = {c->keep_planes, c->force_unfused, c->fused_mode, c->extrema_form, c->three_branches};
     put(dbg, sizeof dbg);
     if (!c->graph_exec || key != c->graph_key) {
         if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
@@ -602,7 +606,7 @@ int sift_b200_create(int device, int max_width, int max_height, sift_b200_ctx** 
         c->fused_mode = v == 2 || v == 3 ? v : 0;
     }
     if (const char* m = getenv("SIFT_B200_CENTER")) c->centred = atoi(m) != 0;   // experiments
-    if (const char* m = getenv("SIFT_B200_GRAPH")) c->use_graph = atoi(m) != 0;
+    if (const char* m = getenv("SIFT_B200_GRAPH")) { c->use_graph = atoi(m) != 0; c->three_branches = atoi(m) == 3; }
     if (const char* m = getenv("SIFT_B200_EXTREMA")) c->extrema_form = atoi(m);
     c->max_w = max_width;
     c->max_h = max_height;

@@ -7,7 +7,11 @@
 // convert_to_grayscale + resize_inter_bilinear (image.cpp:8-24, 62-88) as the input stage.
 //
 // HBM-bound by design: one read of G[i-1], one write of G[i], one write of D[i-1] per level.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 #include "common.cuh"
 #include "kernels.h"
@@ -433,6 +437,25 @@ cudaError_t launch_cascade_t(const CascadeArgs& a, int sm_count, cudaStream_t s)
 
 #include "stream.cuh"
 
+PFN_cuTensorMapEncodeTiled g_stream_encode = nullptr;
+
+cudaError_t stream_make_map(CUtensorMap* map, const float* base, int w, int h, int pitch, int boxw) {
+    const cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)h};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)boxw, 1u};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = g_stream_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides,
+                                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+// SIFT_B200_STREAM_TMA=0 selects the cp.async input path of the streaming kernels (comparison runs)
+bool stream_use_tma() {
+    static const bool on = getenv("SIFT_B200_STREAM_TMA") && atoi(getenv("SIFT_B200_STREAM_TMA")) == 1;   // off until verified
+    return on;
+}
+
 // ------------------------------------------------------------------------------------------
 // Fused input stage for 8-bit gray images: resize_inter_bilinear(2,2) (image.cpp:62-88, optional)
 // + the initial blur (sift.cpp:124, radius 4) in one pass: the up-sampled tile is formed in shared
@@ -603,12 +626,20 @@ cudaError_t pyramid_init() {
     SB_CASC_ATTR(4, 5, 6, 32, 32, 128, 4) SB_CASC_ATTR(8, 10, 0, 32, 32, 128, 4)
     SB_CASC_ATTR(4, 5, 6, 32, 32, 512, 1) SB_CASC_ATTR(8, 10, 0, 32, 32, 512, 1)
 #undef SB_CASC_ATTR
-#define SB_STREAM_ATTR(G, SG)                                                                              \
-    if ((e = cudaFuncSetAttribute(k_stream<G, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmem)) != \
+    if (g_stream_encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if ((e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q)) != cudaSuccess) return e;
+        if (q != cudaDriverEntryPointSuccess || fn == nullptr) return cudaErrorNotSupported;
+        g_stream_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+    }
+#define SB_STREAM_ATTR(G, SG, TM)                                                                          \
+    if ((e = cudaFuncSetAttribute(k_stream<G, SG, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmem)) != \
         cudaSuccess)                                                                                      \
         return e;
-    SB_STREAM_ATTR(StreamA, true) SB_STREAM_ATTR(StreamA, false) SB_STREAM_ATTR(StreamB, true)
-    SB_STREAM_ATTR(StreamB, false)
+    SB_STREAM_ATTR(StreamA, true, true) SB_STREAM_ATTR(StreamA, false, true) SB_STREAM_ATTR(StreamB, true, true)
+    SB_STREAM_ATTR(StreamB, false, true) SB_STREAM_ATTR(StreamA, true, false) SB_STREAM_ATTR(StreamA, false, false)
+    SB_STREAM_ATTR(StreamB, true, false) SB_STREAM_ATTR(StreamB, false, false)
 #undef SB_STREAM_ATTR
 #define SB_INIT(R) if ((e = init_blur_r<R>()) != cudaSuccess) return e;
     SB_INIT(1) SB_INIT(2) SB_INIT(3) SB_INIT(4) SB_INIT(5) SB_INIT(6) SB_INIT(7) SB_INIT(8)

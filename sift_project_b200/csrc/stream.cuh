@@ -53,8 +53,15 @@ struct StreamGeom {
     __host__ __device__ static constexpr int DEPTH(int l) {
         return l == 0 ? K * PF + 2 * R(1) + 3 * K - 1 : 2 * R(l + 1) + 3 * K - 1;
     }
-    __host__ __device__ static constexpr int OFF(int l) { return l <= 0 ? 0 : OFF(l - 1) + DEPTH(l - 1) * W(l - 1); }
-    static constexpr size_t kSmem = (size_t)OFF(NL) * sizeof(float);
+    // The input ring is filled by TMA (cp.async.bulk.tensor.2d): one box per row, or two when the row is wider than
+    // the 256-element box limit; every box lands 128-byte aligned, so the ring's row stride W0S is padded.
+    static constexpr int NBOX = (W(0) + 255) / 256;
+    static constexpr int BOXW = (((W(0) + NBOX - 1) / NBOX) + 31) & ~31;
+    static constexpr int W0S = NBOX * BOXW;
+    __host__ __device__ static constexpr int RS(int l) { return l == 0 ? W0S : W(l); }   // ring row stride of level l
+    __host__ __device__ static constexpr int OFF(int l) { return l <= 0 ? 0 : OFF(l - 1) + DEPTH(l - 1) * RS(l - 1); }
+    static constexpr size_t kRingBytes = (size_t)OFF(NL) * sizeof(float);
+    static constexpr size_t kSmem = kRingBytes + (size_t)DEPTH(0) * 8;   // + one mbarrier per input-ring slot
     static_assert(WS % C == 0 && C % 2 == 0, "strip width / columns per thread");
 };
 
@@ -69,59 +76,112 @@ __device__ __forceinline__ void stream_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// Input rows are fetched by the warps of level 1 (the lightest level): cp.async of one 16-byte chunk per lane
-// (+ a second one for the first few lanes), PF rows ahead; one commit group per step.
-template <class G>
+// Input rows are fetched PF rows ahead into the input ring; ring slot of row r = (r - r0) mod DEPTH(0).
+// TMA form (default): ONE elected thread of level 1 (the lightest level) arms the slot's mbarrier with the row's
+// byte count and issues cp.async.bulk.tensor.2d (NBOX boxes of BOXW x 1 floats) on the plane's tensor map; columns
+// left / right of the image come back as zeros and are never read (BORDER strips clamp their window columns).  The
+// threads of level 1 wait on the slot's mbarrier phase before they read a row.
+// cp.async form (kept for comparison, SIFT_B200_STREAM_TMA=0): every level-1 lane copies 16-byte chunks, one commit
+// group per step, cp.async.wait_group before the CTA barrier.
+__device__ __forceinline__ void stream_mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void stream_mbar_expect(unsigned bar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void stream_mbar_wait(unsigned bar, unsigned parity) {
+    for (unsigned spin = 0;; ++spin) {
+        unsigned done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"   // non-blocking: the bound below is a time bound
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        if (spin > (1u << 22)) __trap();   // a protocol bug traps within a fraction of a second instead of hanging the GPU
+    }
+}
+__device__ __forceinline__ void stream_tma_row(unsigned dst, const CUtensorMap* map, int x, int y, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+
+template <class G, bool TMA>
 struct StreamFetch {
-    static constexpr int W0 = G::W(0), D0 = G::DEPTH(0), NT = 32 * G::WARPS(1), CH = W0 / 4;
+    static constexpr int W0 = G::W(0), W0S = G::W0S, D0 = G::DEPTH(0), NT = 32 * G::WARPS(1), CH = W0 / 4;
     static constexpr int PER = (CH + NT - 1) / NT;
-    const float* src;     // next row to fetch, at this thread's first chunk
-    unsigned dst;         // shared-memory byte address of that chunk in the ring slot of the next row
-    unsigned dst_end;     // ring end (byte address, at this thread's first chunk)
-    int rows_left;
+    const float* src;     // cp.async: next row to fetch, at this thread's first chunk
+    unsigned dst;         // shared-memory byte address of the ring slot of the next row (cp.async: + this thread's chunk)
+    unsigned dst_end;
+    unsigned bar, bar0;   // TMA: mbarrier of that slot / of slot 0
+    int rows_left, row, gx;
     size_t pitch;
     bool ok[PER];
+    bool leader;
 
     __device__ __forceinline__ void init(const CascadeArgs& a, float* smem, int rt, int r0, int rlast, int sx0) {
-        const int gx = sx0 - G::HO(0) + 4 * rt;
-        src = a.in + (size_t)r0 * a.pitch + gx;
-        pitch = a.pitch;
-        const unsigned base = (unsigned)__cvta_generic_to_shared(smem) + 16u * rt;
-        dst = base + (unsigned)((r0 % D0) * W0 * 4);
-        dst_end = base + (unsigned)(D0 * W0 * 4);
+        gx = sx0 - G::HO(0);
         rows_left = rlast - r0 + 1;
+        row = r0;
+        leader = rt == 0;
+        const unsigned base = (unsigned)__cvta_generic_to_shared(smem);
+        if (TMA) {
+            dst = base;
+            dst_end = base + (unsigned)(D0 * W0S * 4);
+            bar0 = bar = base + (unsigned)G::kRingBytes;
+        } else {
+            src = a.in + (size_t)r0 * a.pitch + gx + 4 * rt;
+            pitch = a.pitch;
+            dst = base + 16u * rt;
+            dst_end = dst + (unsigned)(D0 * W0S * 4);
 #pragma unroll
-        for (int k = 0; k < PER; ++k) {
-            const int c = rt + k * NT, x = gx + 4 * k * NT;
-            ok[k] = c < CH && x >= 0 && x < a.pitch;
+            for (int k = 0; k < PER; ++k) {
+                const int c = rt + k * NT, x = gx + 4 * rt + 4 * k * NT;
+                ok[k] = c < CH && x >= 0 && x < a.pitch;
+            }
         }
     }
-    __device__ __forceinline__ void next() {
+    // map: the address of the kernel's __grid_constant__ tensor map, handed down as a plain argument (kept in a
+    // struct member, ptxas lost track of it and fed UTMALDG the wrong uniform register)
+    __device__ __forceinline__ void next(const CUtensorMap* map) {
 #pragma unroll
         for (int kk = 0; kk < G::K; ++kk)
         if (rows_left > 0) {
+            if (TMA) {
+                if (leader) {
+                    stream_mbar_expect(bar, W0S * 4);
 #pragma unroll
-            for (int k = 0; k < PER; ++k)
-                if (ok[k])
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 16u * k * NT),
-                                 "l"(src + 4 * k * NT));
-            src += pitch;
-            dst += W0 * 4;
-            if (dst == dst_end) dst -= D0 * W0 * 4;
+                    for (int b = 0; b < G::NBOX; ++b)
+                        stream_tma_row(dst + (unsigned)(b * G::BOXW * 4), map, gx + b * G::BOXW, row, bar);
+                }
+                ++row;
+                bar += 8;
+            } else {
+#pragma unroll
+                for (int k = 0; k < PER; ++k)
+                    if (ok[k])
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 16u * k * NT),
+                                     "l"(src + 4 * k * NT));
+                src += pitch;
+            }
+            dst += W0S * 4;
+            if (dst == dst_end) { dst -= D0 * W0S * 4; bar = bar0; }
             --rows_left;
         }
-        asm volatile("cp.async.commit_group;\n" ::);
+        if (!TMA) asm volatile("cp.async.commit_group;\n" ::);
     }
 };
 
 // One level of the pipeline, run by the warps of that level.  rt = thread index inside the level.
 // Everything that moves with the row (ring slots, plane offsets) is a running counter: no division, no
 // 64-bit multiply inside the step.
-template <class G, int L, bool BORDER, bool STORE_G>
-__device__ __forceinline__ void stream_level(const CascadeArgs& a, float* smem, const int rt,
+template <class G, int L, bool BORDER, bool STORE_G, bool TMA>
+__device__ __forceinline__ void stream_level(const CascadeArgs& a, const CUtensorMap* tmap, float* smem, const int rt,
                                              const StreamSched& sc, const int sx0) {
     constexpr int R = G::R(L), RA = G::RA(L), C = G::C, C2 = C / 2;
     constexpr int WP = G::W(L - 1), DP = G::DEPTH(L - 1);
+    constexpr int WPS = G::RS(L - 1);   // row stride of the previous level's ring (padded for the input ring)
     constexpr int WL = G::W(L), DL = L < G::NL ? G::DEPTH(L) : 1;
     constexpr bool LAST = L == G::NL;
     const float* ringP = smem + G::OFF(L - 1);
@@ -154,16 +214,21 @@ __device__ __forceinline__ void stream_level(const CascadeArgs& a, float* smem, 
     // running state of the step loop
     constexpr int K = G::K;
     int i = i0;                                            // virtual input row of the first of the K rows of a step
-    int in_off = (min(max(i0, 0), h - 1) % DP) * WP;       // ring slot (floats) of the clamped input row
-    int cen_off = mod(i0 - R, DP) * WP;                    // ... of the previous level's row y (DoG centre)
+    // ring slot (floats) of the clamped input row / of the previous level's row y (DoG centre); the input ring (read
+    // by level 1) counts its rows from the first row fetched, the level rings from row 0
+    const int rbase = L == 1 ? sc.r0 : 0;
+    int in_off = ((min(max(i0, 0), h - 1) - rbase) % DP) * WPS;
+    int cen_off = mod(i0 - R - rbase, DP) * WPS;
+    unsigned in_par = 0;                                   // (TMA) mbarrier phase of the slot at in_off
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)G::kRingBytes;
     int out_off = mod(i0 - R, DL) * WL;                    // ... of this level's row y
     unsigned e_off = (unsigned)((long long)(i0 - R) * a.pitch + gx);   // plane offset of (y, gx); wraps while y < 0
 
-    StreamFetch<G> fetch;
+    StreamFetch<G, TMA> fetch;
     if (L == 1) {
         fetch.init(a, smem, rt, sc.r0, sc.rlast, sx0);
 #pragma unroll 1
-        for (int g = 0; g < G::PF; ++g) fetch.next();
+        for (int g = 0; g < G::PF; ++g) fetch.next(tmap);
     }
 
     // Steady steps: the level is active, every row it reads is inside the image (no clamping) and every row it
@@ -184,6 +249,7 @@ __device__ __forceinline__ void stream_level(const CascadeArgs& a, float* smem, 
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const float* rowp = ringP + in_off;
+            if (TMA && L == 1) stream_mbar_wait(bar0 + 8u * (unsigned)(in_off / WPS), in_par);   // the row has landed
             float v[C + 2 * RA];
             if (!BORDER) {
                 if (C % 4 == 0) {
@@ -216,8 +282,8 @@ __device__ __forceinline__ void stream_level(const CascadeArgs& a, float* smem, 
                 if (c & 1) hv[k][c / 2].y = o; else hv[k][c / 2].x = o;
             }
             if (STEADY || (unsigned)(i + k) < (unsigned)(h - 1)) {   // rows above / below the image re-read the edge row
-                in_off += WP;
-                if (in_off == DP * WP) in_off = 0;
+                in_off += WPS;
+                if (in_off == DP * WPS) { in_off = 0; in_par ^= 1u; }
             }
         }
         // ---- vertical pass, scatter form: row i adds w[|i - y|] * h to every output row y in [i-R, i+R].  The
@@ -311,8 +377,8 @@ __device__ __forceinline__ void stream_level(const CascadeArgs& a, float* smem, 
                 }
             }
             // ---- advance the per-row running state ----
-            cen_off += WP;
-            if (cen_off == DP * WP) cen_off = 0;
+            cen_off += WPS;
+            if (cen_off == DP * WPS) cen_off = 0;
             if (!LAST) {
                 out_off += WL;
                 if (out_off == DL * WL) out_off = 0;
@@ -323,8 +389,8 @@ __device__ __forceinline__ void stream_level(const CascadeArgs& a, float* smem, 
     };
     auto sync_step = [&]() {
         if (L == 1) {
-            fetch.next();
-            stream_wait<G::PF>();
+            fetch.next(tmap);
+            if (!TMA) stream_wait<G::PF>();
         }
         stream_bar();
     };
@@ -346,16 +412,16 @@ __device__ __forceinline__ void stream_level(const CascadeArgs& a, float* smem, 
     }
 }
 
-template <class G, bool BORDER, bool STORE_G>
-__device__ __forceinline__ void stream_body(const CascadeArgs& a, float* smem,
+template <class G, bool BORDER, bool STORE_G, bool TMA>
+__device__ __forceinline__ void stream_body(const CascadeArgs& a, const CUtensorMap* tmap, float* smem,
                                             const StreamSched& sc, int sx0) {
     const int warp = threadIdx.x >> 5;
     if (G::NL >= 3 && warp >= G::FIRSTWARP(3))
-        stream_level<G, (G::NL >= 3 ? 3 : 1), BORDER, STORE_G>(a, smem, threadIdx.x - 32 * G::FIRSTWARP(3), sc, sx0);
+        stream_level<G, (G::NL >= 3 ? 3 : 1), BORDER, STORE_G, TMA>(a, tmap, smem, threadIdx.x - 32 * G::FIRSTWARP(3), sc, sx0);
     else if (warp >= G::FIRSTWARP(2))
-        stream_level<G, 2, BORDER, STORE_G>(a, smem, threadIdx.x - 32 * G::FIRSTWARP(2), sc, sx0);
+        stream_level<G, 2, BORDER, STORE_G, TMA>(a, tmap, smem, threadIdx.x - 32 * G::FIRSTWARP(2), sc, sx0);
     else
-        stream_level<G, 1, BORDER, STORE_G>(a, smem, threadIdx.x, sc, sx0);
+        stream_level<G, 1, BORDER, STORE_G, TMA>(a, tmap, smem, threadIdx.x, sc, sx0);
 }
 
 // Schedule (per CTA, uniform), K rows per step.  Level l consumes the virtual input rows
@@ -373,9 +439,10 @@ __device__ __forceinline__ void stream_body(const CascadeArgs& a, float* smem,
 // and the x-halo reads of the neighbours hit L2).
 // STORE_G: the level planes are stored (always for G1..G3; G4, G5 only for the debug planes); the DoG planes
 // always are.
-template <class G, bool STORE_G>
-__global__ void __launch_bounds__(G::THREADS, G::MINB) k_stream(const CascadeArgs a, const int nseg) {
-    extern __shared__ __align__(16) float smem[];
+template <class G, bool STORE_G, bool TMA>
+__global__ void __launch_bounds__(G::THREADS, G::MINB)
+k_stream(const CascadeArgs a, const __grid_constant__ CUtensorMap tmap, const int nseg) {
+    extern __shared__ __align__(128) float smem[];
     const int strips = (a.w + G::WS - 1) / G::WS;
     auto is_border = [&](int s) { return s * G::WS - G::HO(0) < 0 || s * G::WS + G::WS + G::HO(0) > a.w; };
     long long lo, hi;
@@ -417,6 +484,14 @@ __global__ void __launch_bounds__(G::THREADS, G::MINB) k_stream(const CascadeArg
         if (sc.y0 >= sc.y1) continue;
         if (!first) __syncthreads();   // the rings are reused: the previous pass must be done reading them
         first = false;
+        if (TMA) {   // one mbarrier per input-ring slot, (re)initialised per pass: every slot starts at phase 0
+            if (threadIdx.x == 0) {
+                const unsigned bar0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)G::kRingBytes;
+                for (int q = 0; q < G::DEPTH(0); ++q) stream_mbar_init(bar0 + 8u * q, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+        }
         sc.f[G::NL] = sc.y0;
         sc.e[G::NL] = sc.y1 - 1;
 #pragma unroll
@@ -434,10 +509,14 @@ __global__ void __launch_bounds__(G::THREADS, G::MINB) k_stream(const CascadeArg
             if (l < G::NL) sc.T[l + 1] = sc.T[l] + 1 + (sc.f[l] + G::K - 1 + G::R(l) - sc.i0[l]) / G::K;
         }
         sc.steps = sc.Tend[G::NL] + 1;
+        // level 1 consumes K rows per step: with K > 1 its last step may touch one row beyond the last row it needs.
+        // The cp.async form reads whatever the slot holds (the value is never used); the TMA form WAITS for the row
+        // to land, so the row has to be requested as well.
+        sc.rlast = min(max(sc.rlast, sc.i0[1] + (sc.Tend[1] - sc.T[1] + 1) * G::K - 1), a.h - 1);
         if (border)
-            stream_body<G, true, STORE_G>(a, smem, sc, s * G::WS);
+            stream_body<G, true, STORE_G, TMA>(a, &tmap, smem, sc, s * G::WS);
         else
-            stream_body<G, false, STORE_G>(a, smem, sc, s * G::WS);
+            stream_body<G, false, STORE_G, TMA>(a, &tmap, smem, sc, s * G::WS);
     }
 }
 
@@ -447,6 +526,10 @@ __global__ void __launch_bounds__(G::THREADS, G::MINB) k_stream(const CascadeArg
 // two independent rows in the horizontal pass), 3 CTAs per SM.  Measured alternatives in DESIGN.md.
 using StreamA = StreamGeom<3, 4, 5, 6, 4, 96, 12, 5, true, 1>;    // G0 -> G1,G2,G3, D0,D1,D2, next base
 using StreamB = StreamGeom<2, 8, 10, 0, 4, 232, 6, 3, true, 2>;   // G3 -> (G4,G5) -> D3,D4
+
+// 2-D tensor map of one FP32 plane (w x h, `pitch` floats per row) with a BOXW x 1 box, no swizzle, zero fill
+cudaError_t stream_make_map(CUtensorMap* map, const float* base, int w, int h, int pitch, int boxw);
+bool stream_use_tma();
 
 template <class G>
 cudaError_t launch_stream_t(const CascadeArgs& a, int sm_count, cudaStream_t s, int force = 0) {
@@ -470,9 +553,19 @@ cudaError_t launch_stream_t(const CascadeArgs& a, int sm_count, cudaStream_t s, 
     }
     for (int l = 0; l < G::NL; ++l)
         if (a.d[l] == nullptr || (a.g[l] == nullptr) != (a.g[0] == nullptr)) return cudaErrorInvalidValue;
-    if (a.g[0] != nullptr)
-        k_stream<G, true><<<ctas, G::THREADS, G::kSmem, s>>>(a, nseg);
-    else
-        k_stream<G, false><<<ctas, G::THREADS, G::kSmem, s>>>(a, nseg);
+    CUtensorMap map;
+    memset(&map, 0, sizeof map);
+    const bool tma = stream_use_tma();
+    if (tma) {
+        const cudaError_t e = stream_make_map(&map, a.in, a.w, a.h, a.pitch, G::BOXW);
+        if (e != cudaSuccess) return e;
+    }
+    if (a.g[0] != nullptr) {
+        if (tma) k_stream<G, true, true><<<ctas, G::THREADS, G::kSmem, s>>>(a, map, nseg);
+        else k_stream<G, true, false><<<ctas, G::THREADS, G::kSmem, s>>>(a, map, nseg);
+    } else {
+        if (tma) k_stream<G, false, true><<<ctas, G::THREADS, G::kSmem, s>>>(a, map, nseg);
+        else k_stream<G, false, false><<<ctas, G::THREADS, G::kSmem, s>>>(a, map, nseg);
+    }
     return cudaGetLastError();
 }
