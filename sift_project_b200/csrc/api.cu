@@ -73,6 +73,7 @@ struct sift_b200_ctx {
     // extrema scan of each octave on a side stream, so the small octaves overlap the large ones ----
     bool use_graph = true;
     bool three_branches = false; // experiments (SIFT_B200_GRAPH=3): extrema scans on a third graph branch
+    long long fork_min_px = 1ll << 20;   // octaves of at least this many pixels run their second half on the side branch
     int extrema_form = 0;        // 0 = four columns per lane (default), 1 = one column per lane
     cudaStream_t side = nullptr, side2 = nullptr;
     std::vector<cudaEvent_t> fork_ev;   // [0 .. kMaxOctaves): "octave chain reached o"; [kMaxOctaves]: join of the
@@ -272,12 +273,16 @@ struct DetectPlan {
 
 int enqueue_body(sift_b200_ctx* c, const DetectPlan& pl, bool forked, int* n_launches, int* stage_launches) {
     const StageParams& sp = c->sp;
-    // (a third branch for the extrema scans was measured and dropped: 4K latency 1.64 ms against 1.60 ms with two
-    // branches, batch throughput -4 %: the scans then compete with the next octave's cascade kernels for the SMs)
+    // Branches of the graph: the octave chain (first cascade kernel of every octave) on the main stream; the second
+    // cascade kernel + extrema scan of the LARGE octaves on the side stream; those of the small octaves follow their
+    // octave on the main stream, which would otherwise idle once the chain is through -- the two branches then
+    // carry about the same time (4K: 0.50 / 0.48 ms).  (A third branch for the extrema scans was measured and
+    // dropped: 4K latency 1.64 ms against 1.60 ms, batch throughput -4 %: the scans then compete with the next
+    // octave's cascade kernels for the SMs.)
     const bool three = forked && c->three_branches;
-    cudaStream_t s = c->stream, s2 = forked ? c->side : c->stream, s3 = three ? c->side2 : s2;
+    cudaStream_t s = c->stream;
     int total = 0;
-    bool s3_forked = false;
+    bool side_forked = false, s3_forked = false;
     auto mark = [&](int stage, int launches) {
         total += launches;
         if (stage_launches) stage_launches[stage] += launches;
@@ -285,6 +290,8 @@ int enqueue_body(sift_b200_ctx* c, const DetectPlan& pl, bool forked, int* n_lau
     };
     for (int o = 0; o < pl.octaves; ++o) {
         OctaveDesc& od = c->pyr.oct[o];
+        const bool on_side = forked && (long long)od.w * od.h >= c->fork_min_px;
+        cudaStream_t s2 = on_side ? c->side : s, s3 = (three && on_side) ? c->side2 : s2;
         float* dec = nullptr;
         int dw = 0, dh = 0, dp = 0;
         if (o + 1 < pl.octaves) {  // next base = G[layers-3] decimated, sift.cpp:195-196
@@ -293,9 +300,10 @@ int enqueue_body(sift_b200_ctx* c, const DetectPlan& pl, bool forked, int* n_lau
         }
         if (pl.fused) {
             CU(c, launch_octave_fused(od, pl.taps, dec, dw, dh, dp, c->keep_planes, c->sm_count, c->fused_mode, 1, s));
-            if (forked) {
+            if (on_side) {
                 CU(c, cudaEventRecord(c->fork_ev[o], s));
                 CU(c, cudaStreamWaitEvent(s2, c->fork_ev[o], 0));
+                side_forked = true;
             }
             if (o == 0) mark(SIFT_B200_STAGE_PYRAMID, 1);   // the two largest launches are timed one by one
             CU(c, launch_octave_fused(od, pl.taps, dec, dw, dh, dp, c->keep_planes, c->sm_count, c->fused_mode, 2, s2));
@@ -306,14 +314,15 @@ int enqueue_body(sift_b200_ctx* c, const DetectPlan& pl, bool forked, int* n_lau
                 CU(c, launch_blur(od.G[i - 1], od.G[i], od.D[i - 1], last ? dec : nullptr, od.w, od.h, od.pitch,
                                   last ? dw : 0, last ? dh : 0, last ? dp : 0, pl.taps[i], s));
             }
-            if (forked) {
+            if (on_side) {
                 CU(c, cudaEventRecord(c->fork_ev[o], s));
                 CU(c, cudaStreamWaitEvent(s2, c->fork_ev[o], 0));
+                side_forked = true;
             }
             mark(SIFT_B200_STAGE_PYRAMID, pl.layers - 1);
         }
         if (od.w >= 2 * sp.border + 1 && od.h >= 2 * sp.border + 1) {
-            if (three) {   // the extrema scans form a third branch: octave o's scan only waits for octave o's planes
+            if (three && on_side) {   // experiments: the extrema scans of the large octaves as a third branch
                 CU(c, cudaEventRecord(c->fork_ev[kMaxOctaves + 1 + o], s2));
                 CU(c, cudaStreamWaitEvent(s3, c->fork_ev[kMaxOctaves + 1 + o], 0));
                 s3_forked = true;
@@ -322,13 +331,13 @@ int enqueue_body(sift_b200_ctx* c, const DetectPlan& pl, bool forked, int* n_lau
             mark(SIFT_B200_STAGE_EXTREMA, 1);
         }
     }
-    if (forked) {
-        CU(c, cudaEventRecord(c->fork_ev[kMaxOctaves], s2));
+    if (side_forked) {
+        CU(c, cudaEventRecord(c->fork_ev[kMaxOctaves], c->side));
         CU(c, cudaStreamWaitEvent(s, c->fork_ev[kMaxOctaves], 0));
-        if (s3_forked) {
-            CU(c, cudaEventRecord(c->fork_ev[2 * kMaxOctaves + 1], s3));
-            CU(c, cudaStreamWaitEvent(s, c->fork_ev[2 * kMaxOctaves + 1], 0));
-        }
+    }
+    if (s3_forked) {
+        CU(c, cudaEventRecord(c->fork_ev[2 * kMaxOctaves + 1], c->side2));
+        CU(c, cudaStreamWaitEvent(s, c->fork_ev[2 * kMaxOctaves + 1], 0));
     }
     CU(c, launch_refine(c->d_pyr, c->d_cands, c->d_raw, c->d_counters, sp, c->sm_count, s));
     mark(SIFT_B200_STAGE_REFINE, 1);
@@ -467,7 +476,8 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     std::vector<uint8_t> key;
     auto put = [&](const void* q, size_t n) { key.insert(key.end(), (const uint8_t*)q, (const uint8_t*)q + n); };
     put(&pl, sizeof pl); put(&sp, sizeof sp); put(&c->pyr, sizeof c->pyr); put(&c->ss.nb, sizeof(int));
-    const int dbg[5] = {c->keep_planes, c->force_unfused, c->fused_mode, c->extrema_form, c->three_branches};
+    const int dbg[6] = {c->keep_planes, c->force_unfused, c->fused_mode, c->extrema_form, c->three_branches,
+                        (int)std::min<long long>(c->fork_min_px, 1ll << 30)};
     put(dbg, sizeof dbg);
     if (!c->graph_exec || key != c->graph_key) {
         if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
@@ -608,6 +618,7 @@ int sift_b200_create(int device, int max_width, int max_height, sift_b200_ctx** 
     if (const char* m = getenv("SIFT_B200_CENTER")) c->centred = atoi(m) != 0;   // experiments
     if (const char* m = getenv("SIFT_B200_GRAPH")) { c->use_graph = atoi(m) != 0; c->three_branches = atoi(m) == 3; }
     if (const char* m = getenv("SIFT_B200_EXTREMA")) c->extrema_form = atoi(m);
+    if (const char* m = getenv("SIFT_B200_FORK_MIN_PX")) c->fork_min_px = atoll(m);
     c->max_w = max_width;
     c->max_h = max_height;
 #define CRT(call)                                                                                   \

@@ -634,7 +634,7 @@ cudaError_t pyramid_init() {
         g_stream_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
     }
 #define SB_STREAM_ATTR(G, SG, TM)                                                                          \
-    if ((e = cudaFuncSetAttribute(k_stream<G, SG, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmem)) != \
+    if ((e = cudaFuncSetAttribute(k_stream<G, SG, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamLayout<G, TM>::kSmem)) != \
         cudaSuccess)                                                                                      \
         return e;
     SB_STREAM_ATTR(StreamA, true, true) SB_STREAM_ATTR(StreamA, false, true) SB_STREAM_ATTR(StreamB, true, true)

@@ -57,12 +57,18 @@ struct StreamGeom {
     // the 256-element box limit; every box lands 128-byte aligned, so the ring's row stride W0S is padded.
     static constexpr int NBOX = (W(0) + 255) / 256;
     static constexpr int BOXW = (((W(0) + NBOX - 1) / NBOX) + 31) & ~31;
-    static constexpr int W0S = NBOX * BOXW;
-    __host__ __device__ static constexpr int RS(int l) { return l == 0 ? W0S : W(l); }   // ring row stride of level l
-    __host__ __device__ static constexpr int OFF(int l) { return l <= 0 ? 0 : OFF(l - 1) + DEPTH(l - 1) * RS(l - 1); }
-    static constexpr size_t kRingBytes = (size_t)OFF(NL) * sizeof(float);
-    static constexpr size_t kSmem = kRingBytes + (size_t)DEPTH(0) * 8;   // + one mbarrier per input-ring slot
     static_assert(WS % C == 0 && C % 2 == 0, "strip width / columns per thread");
+};
+
+// Shared-memory layout of the rings; only the TMA form pads the input ring (and carries the mbarriers): the padding
+// costs 2-6 KB per CTA, which matters for how many kernels of OTHER images fit beside this one on an SM.
+template <class G, bool TMA>
+struct StreamLayout {
+    static constexpr int W0S = TMA ? G::NBOX * G::BOXW : G::W(0);
+    __host__ __device__ static constexpr int RS(int l) { return l == 0 ? W0S : G::W(l); }   // ring row stride of level l
+    __host__ __device__ static constexpr int OFF(int l) { return l <= 0 ? 0 : OFF(l - 1) + G::DEPTH(l - 1) * RS(l - 1); }
+    static constexpr size_t kRingBytes = (size_t)OFF(G::NL) * sizeof(float);
+    static constexpr size_t kSmem = kRingBytes + (TMA ? (size_t)G::DEPTH(0) * 8 : 0);   // + one mbarrier per input-ring slot
 };
 
 __device__ __forceinline__ void stream_bar() {
@@ -109,7 +115,7 @@ __device__ __forceinline__ void stream_tma_row(unsigned dst, const CUtensorMap* 
 
 template <class G, bool TMA>
 struct StreamFetch {
-    static constexpr int W0 = G::W(0), W0S = G::W0S, D0 = G::DEPTH(0), NT = 32 * G::WARPS(1), CH = W0 / 4;
+    static constexpr int W0 = G::W(0), W0S = StreamLayout<G, TMA>::W0S, D0 = G::DEPTH(0), NT = 32 * G::WARPS(1), CH = W0 / 4;
     static constexpr int PER = (CH + NT - 1) / NT;
     const float* src;     // cp.async: next row to fetch, at this thread's first chunk
     unsigned dst;         // shared-memory byte address of the ring slot of the next row (cp.async: + this thread's chunk)
@@ -129,7 +135,7 @@ struct StreamFetch {
         if (TMA) {
             dst = base;
             dst_end = base + (unsigned)(D0 * W0S * 4);
-            bar0 = bar = base + (unsigned)G::kRingBytes;
+            bar0 = bar = base + (unsigned)StreamLayout<G, TMA>::kRingBytes;
         } else {
             src = a.in + (size_t)r0 * a.pitch + gx + 4 * rt;
             pitch = a.pitch;
@@ -181,11 +187,12 @@ __device__ __forceinline__ void stream_level(const CascadeArgs& a, const CUtenso
                                              const StreamSched& sc, const int sx0) {
     constexpr int R = G::R(L), RA = G::RA(L), C = G::C, C2 = C / 2;
     constexpr int WP = G::W(L - 1), DP = G::DEPTH(L - 1);
-    constexpr int WPS = G::RS(L - 1);   // row stride of the previous level's ring (padded for the input ring)
+    using LY = StreamLayout<G, TMA>;
+    constexpr int WPS = LY::RS(L - 1);   // row stride of the previous level's ring (padded for the TMA input ring)
     constexpr int WL = G::W(L), DL = L < G::NL ? G::DEPTH(L) : 1;
     constexpr bool LAST = L == G::NL;
-    const float* ringP = smem + G::OFF(L - 1);
-    float* ringL = smem + (LAST ? 0 : G::OFF(L));
+    const float* ringP = smem + LY::OFF(L - 1);
+    float* ringL = smem + (LAST ? 0 : LY::OFF(L));
     const BlurTaps& tp = a.taps[L - 1];
     const int w = a.w, h = a.h;
 
@@ -220,7 +227,7 @@ __device__ __forceinline__ void stream_level(const CascadeArgs& a, const CUtenso
     int in_off = ((min(max(i0, 0), h - 1) - rbase) % DP) * WPS;
     int cen_off = mod(i0 - R - rbase, DP) * WPS;
     unsigned in_par = 0;                                   // (TMA) mbarrier phase of the slot at in_off
-    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)G::kRingBytes;
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)LY::kRingBytes;
     int out_off = mod(i0 - R, DL) * WL;                    // ... of this level's row y
     unsigned e_off = (unsigned)((long long)(i0 - R) * a.pitch + gx);   // plane offset of (y, gx); wraps while y < 0
 
@@ -486,7 +493,7 @@ k_stream(const CascadeArgs a, const __grid_constant__ CUtensorMap tmap, const in
         first = false;
         if (TMA) {   // one mbarrier per input-ring slot, (re)initialised per pass: every slot starts at phase 0
             if (threadIdx.x == 0) {
-                const unsigned bar0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)G::kRingBytes;
+                const unsigned bar0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)StreamLayout<G, TMA>::kRingBytes;
                 for (int q = 0; q < G::DEPTH(0); ++q) stream_mbar_init(bar0 + 8u * q, 1);
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             }
@@ -561,11 +568,11 @@ cudaError_t launch_stream_t(const CascadeArgs& a, int sm_count, cudaStream_t s, 
         if (e != cudaSuccess) return e;
     }
     if (a.g[0] != nullptr) {
-        if (tma) k_stream<G, true, true><<<ctas, G::THREADS, G::kSmem, s>>>(a, map, nseg);
-        else k_stream<G, true, false><<<ctas, G::THREADS, G::kSmem, s>>>(a, map, nseg);
+        if (tma) k_stream<G, true, true><<<ctas, G::THREADS, StreamLayout<G, true>::kSmem, s>>>(a, map, nseg);
+        else k_stream<G, true, false><<<ctas, G::THREADS, StreamLayout<G, false>::kSmem, s>>>(a, map, nseg);
     } else {
-        if (tma) k_stream<G, false, true><<<ctas, G::THREADS, G::kSmem, s>>>(a, map, nseg);
-        else k_stream<G, false, false><<<ctas, G::THREADS, G::kSmem, s>>>(a, map, nseg);
+        if (tma) k_stream<G, false, true><<<ctas, G::THREADS, StreamLayout<G, true>::kSmem, s>>>(a, map, nseg);
+        else k_stream<G, false, false><<<ctas, G::THREADS, StreamLayout<G, false>::kSmem, s>>>(a, map, nseg);
     }
     return cudaGetLastError();
 }

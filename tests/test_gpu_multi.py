@@ -97,6 +97,48 @@ def test_drop_in_sift_binary(tmp_path):
         assert differing < 2e-3, (name, differing)       # a ring or spoke end that rounds to the next pixel
 
 
+def test_file_batch_pipeline_equals_per_image_detect(tmp_path):
+    """image files -> the reference's decoder on host threads (image_io.cpp:20-35) -> page-locked
+    ring -> asynchronous H2D -> detect on a ring of contexts (sift_project_b200/shim/sift_batch.cpp).  Same records
+    as one detect call per image, in file order; RGB and gray files of different sizes mixed."""
+    import numpy as np
+    from PIL import Image
+    exe = os.path.join(ROOT, "oracle", "_ref", "sift_batch")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/sift_batch is built only where /root/reference exists")
+    sys.path.insert(0, ROOT)
+    import sift_project_b200 as S
+    from oracle import oracle as O
+    g = os.path.join(ROOT, "tests", "golden")
+    files = [os.path.join(g, "image1.png"), os.path.join(g, "image2.png")]
+    for k, (h, w) in enumerate(((240, 320), (300, 200), (480, 640))):
+        f = tmp_path / f"synth{k}.png"
+        Image.fromarray(O.synth_image(h, w, seed=90 + k)).save(f)
+        files.append(str(f))
+    files = files + files[:3]
+    env = dict(os.environ, SIFT_BATCH_CONTEXTS="2", SIFT_BATCH_DECODERS="3")
+    out = subprocess.run([exe] + files, capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if "keypoints, records" in l]
+    assert len(lines) == len(files)
+
+    def fnv(b):
+        h = 1469598103934665603
+        for x in b:
+            h = ((h ^ x) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+
+    with S.SiftContext(755, 640) as c:
+        for f, line in zip(files, lines):
+            px = np.asarray(Image.open(f))
+            want = c.detect(px)
+            assert line.startswith(f + ": ")
+            n, digest = int(line.split(": ")[1].split(" ")[0]), int(line.rsplit(" ", 1)[1], 16)
+            assert n == len(want), (f, n, len(want))
+            assert digest == fnv(want.tobytes()), f
+    print([l for l in out.stdout.splitlines() if l.startswith("batch:")][0])
+
+
 def test_collection_driver_on_a_synthetic_dataset(tmp_path):
     """overlapping crops of one scene + a STITCH-GRAPH file -> detect all, match
     the listed edges; overlapping neighbours share many matches, and every edge equals the oracle."""
