@@ -50,7 +50,8 @@ class _Stats(C.Structure):
 
 
 def library_path():
-    return os.path.join(HERE, "libsift_b200.so")
+    # SIFT_B200_LIB: another build of the same library (kernel experiments); never a different implementation
+    return os.environ.get("SIFT_B200_LIB") or os.path.join(HERE, "libsift_b200.so")
 
 
 def declared_symbols():

@@ -73,7 +73,7 @@ struct sift_b200_ctx {
     // extrema scan of each octave on a side stream, so the small octaves overlap the large ones ----
     bool use_graph = true;
     bool three_branches = false; // experiments (SIFT_B200_GRAPH=3): extrema scans on a third graph branch
-    long long fork_min_px = 1ll << 20;   // octaves of at least this many pixels run their second half on the side branch
+    long long fork_min_px = 300000;   // octaves of at least this many pixels run their second half on the side branch
     int extrema_form = 0;        // 0 = four columns per lane (default), 1 = one column per lane
     cudaStream_t side = nullptr, side2 = nullptr;
     std::vector<cudaEvent_t> fork_ev;   // [0 .. kMaxOctaves): "octave chain reached o"; [kMaxOctaves]: join of the
@@ -276,7 +276,7 @@ int enqueue_body(sift_b200_ctx* c, const DetectPlan& pl, bool forked, int* n_lau
     // Branches of the graph: the octave chain (first cascade kernel of every octave) on the main stream; the second
     // cascade kernel + extrema scan of the LARGE octaves on the side stream; those of the small octaves follow their
     // octave on the main stream, which would otherwise idle once the chain is through -- the two branches then
-    // carry about the same time (4K: 0.50 / 0.48 ms).  (A third branch for the extrema scans was measured and
+    // carry about the same time (measured at 4K, latency by threshold: every octave on the side 1.596 ms, >= 4 Mpx 1.615, >= 1 Mpx 1.566, >= 0.3 Mpx 1.547).  (A third branch for the extrema scans was measured and
     // dropped: 4K latency 1.64 ms against 1.60 ms, batch throughput -4 %: the scans then compete with the next
     // octave's cascade kernels for the SMs.)
     const bool three = forked && c->three_branches;
