@@ -498,6 +498,12 @@ def run_b200(args):
                 t = marks_acc[idx] / reps
                 per_kernel.append({"kernel": name, "ms": t, "algorithmic_bytes": bpp * px0,
                                    "achieved": bpp * px0 / (t * 1e-3) / 1e9, "frac": bpp * px0 / (t * 1e-3) / 1e9 / hbm_peak})
+            ex0 = pyr_marks[1] + 1   # the mark after octave 0's second cascade kernel is octave 0's extrema scan
+            if ex0 < len(marks) and marks[ex0][0] == "extrema":
+                t = marks_acc[ex0] / reps
+                per_kernel.append({"kernel": "octave 0: 3x3x3 extrema scan (k_extrema4), reads D0..D4", "ms": t,
+                                   "algorithmic_bytes": 20.0 * px0, "achieved": 20.0 * px0 / (t * 1e-3) / 1e9,
+                                   "frac": 20.0 * px0 / (t * 1e-3) / 1e9 / hbm_peak})
         roof = {"bound": "hbm", "kernel": "pyramid: fused cascade G0->G1..G3,D0..D2,next base + G3->D3,D4 (k_stream on octaves >= 2 Mpx, k_cascade below), all octaves of one image", "achieved": achieved,
                 "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                 "algorithmic_bytes": pyr_bytes, "ms": stages["pyramid"], "launches": nl["pyramid"],

@@ -177,6 +177,18 @@ class SiftContext:
         if rc:
             raise SiftError(rc, self._L.sift_b200_last_error(self._h).decode())
 
+    def _after_torch(self, *tensors):
+        """Stream contract of the C ABI (sift_b200.h): device pointers are consumed in the CONTEXT's stream order.
+        A torch CUDA tensor was produced on torch's current stream, so the context's stream is made to wait for
+        an event recorded there before any call that reads it (no host synchronisation)."""
+        if not any(hasattr(t, "is_cuda") and t.is_cuda for t in tensors):
+            return
+        import torch
+        dev = next(t.device for t in tensors if hasattr(t, "is_cuda") and t.is_cuda)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        torch.cuda.ExternalStream(self.stream, device=dev).wait_event(ev)
+
     # ---- detect_keypoints_and_descriptors ----
     def detect(self, image, capacity=None, **params):
         """image: HxW or HxWx3, uint8 or float (0..255), numpy (host) or torch CUDA tensor."""
@@ -197,6 +209,7 @@ class SiftContext:
                 fn = self._L.sift_b200_detect_u8
             else:
                 arr, fn = arr.float(), self._L.sift_b200_detect_f32
+            self._after_torch(arr)
         cap = capacity if capacity is not None else max(4096, (w * h) // 16)
         while True:
             out = np.zeros(cap, dtype=KP_DTYPE)
@@ -211,6 +224,7 @@ class SiftContext:
     def detect_enqueue(self, image_u8, width, height, channels=1, **params):
         """image_u8: torch CUDA tensor, (pinned) host array / tensor, or a raw pointer."""
         p = make_params(**params)
+        self._after_torch(image_u8)
         self._check(self._L.sift_b200_detect_enqueue_u8(self._h, _ptr(image_u8), width, height, channels,
                                                         C.byref(p)))
 
@@ -266,12 +280,14 @@ class SiftContext:
         cap = max(na, 1)
         ia, ib, d = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float64)
         n = C.c_int(0)
+        self._after_torch(desc_a, desc_b)
         self._check(self._L.sift_b200_match(self._h, _ptr(desc_a) if na else None, na,
                                             _ptr(desc_b) if nb else None, nb, float(ratio_threshold),
                                             ia.ctypes.data, ib.ctypes.data, d.ctypes.data, cap, C.byref(n)))
         return ia[: n.value].copy(), ib[: n.value].copy(), d[: n.value].copy()
 
     def match_enqueue(self, d_a, na, d_b, nb, d_best_idx, d_best_d2, d_second_d2):
+        self._after_torch(d_a, d_b, d_best_idx, d_best_d2, d_second_d2)
         self._check(self._L.sift_b200_match_enqueue(self._h, _ptr(d_a), na, _ptr(d_b), nb, _ptr(d_best_idx),
                                                     _ptr(d_best_d2), _ptr(d_second_d2)))
 
@@ -308,6 +324,7 @@ class SiftContext:
         ptrs = (C.c_void_p * max(len(keep), 1))(*[(_ptr(d) if d.shape[0] else None) for d in keep])
         counts = (C.c_int32 * max(len(keep), 1))(*[int(d.shape[0]) for d in keep])
         n = C.c_int(0)
+        self._after_torch(*keep)
         self._check(self._L.sift_b200_collection_match(self._h, n_images, ptrs, counts, int(both_directions), C.byref(n)))
         self._coll_keep = keep   # host sources must outlive the asynchronous copies
         return n.value
