@@ -232,6 +232,12 @@ int sift_b200_debug_keypoints(sift_b200_ctx* ctx, int stage, sift_b200_keypoint*
 int sift_b200_debug_orient(sift_b200_ctx* ctx, const sift_b200_keypoint* raw_in, int n, sift_b200_keypoint* out,
                            int capacity, int* count);
 int sift_b200_debug_describe(sift_b200_ctx* ctx, sift_b200_keypoint* inout, int n);
+/* Write audit of the scale-space kernels (there is no sanitizer on the GPU pool): arm fills the whole arena with a
+ * NaN pattern; after the NEXT detect call, check returns how many elements the pipeline must not write (row padding
+ * of every plane, planes kept on chip, the arena behind the last plane) lost the pattern, and how many elements it
+ * must write still hold it.  Both must be 0. */
+int sift_b200_debug_canary_arm(sift_b200_ctx* ctx);
+int sift_b200_debug_canary_check(sift_b200_ctx* ctx, int64_t* stray_writes, int64_t* missing_writes);
 /* Launch plan switches (each: 0 / 1, or -1 to leave unchanged).  use_graph (default 1; env SIFT_B200_GRAPH): the
  * stages after the input kernel are captured once per (image size, parameters) into a CUDA graph -- octave chain on
  * one branch, second cascade kernel + extrema of each octave on another -- and replayed with one launch per image;

@@ -116,6 +116,8 @@ def load_library():
         "sift_b200_debug_orient": (i32, [vp, vp, i32, vp, i32, i32p]),
         "sift_b200_debug_describe": (i32, [vp, vp, i32]),
         "sift_b200_debug_launch_plan": (i32, [vp, i32, i32, i32]),
+        "sift_b200_debug_canary_arm": (i32, [vp]),
+        "sift_b200_debug_canary_check": (i32, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         "sift_b200_result_copy": (i32, [vp, vp, i32, i32p]),
         "sift_b200_set_profiling": (i32, [vp, i32]),
         "sift_b200_get_profile": (i32, [vp, vp, vp]),
@@ -384,6 +386,15 @@ class SiftContext:
         self._check(self._L.sift_b200_debug_launch_plan(self._h, -1 if use_graph is None else int(use_graph),
                                                         -1 if centred is None else int(centred),
                                                         -1 if extrema_form is None else int(extrema_form)))
+
+    def canary_arm(self):
+        self._check(self._L.sift_b200_debug_canary_arm(self._h))
+
+    def canary_check(self):
+        """(stray writes, missing writes) of the scale-space kernels since canary_arm(); both must be 0."""
+        a, b = C.c_int64(-1), C.c_int64(-1)
+        self._check(self._L.sift_b200_debug_canary_check(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     @property
     def graphs_built(self):

@@ -1082,6 +1082,61 @@ int sift_b200_debug_describe(sift_b200_ctx* c, sift_b200_keypoint* inout, int n)
     return SIFT_B200_OK;
 }
 
+// Canary audit: sift_b200_debug_canary_arm fills the whole scale-space arena with a NaN pattern; after the next
+// detect call sift_b200_debug_canary_check counts (a) elements the pipeline had no business writing -- row padding
+// (w <= x < pitch) of every plane, planes that stay on chip (G[4], G[5] unless kept), the arena behind the last plane
+// -- that no longer hold the pattern, and (b) elements inside the planes it must write that still hold it.
+static const unsigned kCanary = 0x7fc0beefu;   // a quiet NaN no kernel produces
+
+int sift_b200_debug_canary_arm(sift_b200_ctx* c) {
+    if (!c) return SIFT_B200_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, launch_canary_fill(c->arena, c->arena_floats, kCanary, c->sm_count, c->stream));
+    c->pyramid_valid = false;
+    c->launches += 1;
+    return SIFT_B200_OK;
+}
+
+int sift_b200_debug_canary_check(sift_b200_ctx* c, int64_t* stray_writes, int64_t* missing_writes) {
+    if (!c || !stray_writes || !missing_writes) return SIFT_B200_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    int rc = debug_stage_ready(c);
+    if (rc) return rc;
+    unsigned long long* d_counts = nullptr;
+    CU(c, cudaMalloc(&d_counts, 2 * sizeof(unsigned long long)));
+    cudaStream_t s = c->stream;
+    cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned long long), s);
+    const float* end = c->arena;
+    const bool fused = c->sp.intervals == 3 && !c->force_unfused;
+    for (int o = 0; o < c->pyr.octaves; ++o) {
+        const OctaveDesc& od = c->pyr.oct[o];
+        for (int i = 0; i < c->layers; ++i) {
+            // the fused cascades keep the last two Gaussian levels on chip (unless the debug planes are on); the
+            // per-level path writes every level; octave 0's last level is the input stage's scratch plane there
+            const bool on_chip = fused && !c->keep_planes && i >= c->layers - 2;
+            const bool scratch = o == 0 && i == c->layers - 1 && !fused;
+            launch_canary_plane(od.G[i], od.w, od.h, od.pitch, kCanary, (on_chip || scratch) ? (scratch ? 1 : 0) : 1, d_counts, c->sm_count, s);
+            end = std::max(end, (const float*)(od.G[i] + (size_t)od.pitch * od.h));
+        }
+        for (int i = 0; i < c->dogs; ++i) {
+            launch_canary_plane(od.D[i], od.w, od.h, od.pitch, kCanary, 1, d_counts, c->sm_count, s);
+            end = std::max(end, (const float*)(od.D[i] + (size_t)od.pitch * od.h));
+        }
+    }
+    const size_t used = (size_t)(end - c->arena);
+    if (used < c->arena_floats)
+        launch_canary_tail(end, c->arena_floats - used, kCanary, d_counts, c->sm_count, s);
+    unsigned long long h[2] = {0, 0};
+    cudaError_t e = cudaMemcpyAsync(h, d_counts, sizeof h, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_counts);
+    if (e != cudaSuccess) return fail(c, SIFT_B200_E_CUDA, "canary check failed: %s", cudaGetErrorString(e));
+    *stray_writes = (int64_t)h[0];
+    *missing_writes = (int64_t)h[1];
+    return SIFT_B200_OK;
+}
+
 int sift_b200_debug_launch_plan(sift_b200_ctx* c, int use_graph, int centred, int extrema_form) {
     if (!c) return SIFT_B200_E_INVALID;
     if (use_graph >= 0) c->use_graph = use_graph != 0;

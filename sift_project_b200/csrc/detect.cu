@@ -878,7 +878,58 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Canary audit (debug): the arena is filled with a NaN pattern before a detect call; afterwards every element of a
+// plane the pipeline writes must have been overwritten inside the image (x < w) and must still hold the pattern in
+// the row padding (w <= x < pitch).  Catches out-of-bounds and missed stores of the scale-space kernels without a
+// sanitizer.  counts[0] = padding elements overwritten, counts[1] = image elements never written.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_canary_fill(unsigned* __restrict__ p, size_t n, unsigned pattern) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = pattern;
+}
+__global__ void __launch_bounds__(256) k_canary_plane(const unsigned* __restrict__ plane, int w, int h, int pitch,
+                                                       unsigned pattern, int expect_written,
+                                                       unsigned long long* __restrict__ counts) {
+    unsigned long long bad_pad = 0, unwritten = 0;
+    const size_t n = (size_t)pitch * h;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % (size_t)pitch);
+        const bool is_pattern = plane[i] == pattern;
+        // (a row's last float4 store may spill into the first 1-3 padding floats when w is not a multiple of 4:
+        // by design, the pitch is a multiple of 32 floats; everything from round_up(w, 4) on must be untouched)
+        if (x >= ((w + 3) & ~3)) bad_pad += is_pattern ? 0 : 1;
+        else if (x >= w) continue;
+        else if (expect_written) unwritten += is_pattern ? 1 : 0;
+        else bad_pad += is_pattern ? 0 : 1;          // a plane nobody may write at all
+    }
+    if (bad_pad) atomicAdd(&counts[0], bad_pad);
+    if (unwritten) atomicAdd(&counts[1], unwritten);
+}
+__global__ void __launch_bounds__(256) k_canary_tail(const unsigned* __restrict__ p, size_t n, unsigned pattern,
+                                                      unsigned long long* __restrict__ counts) {
+    unsigned long long bad = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        bad += p[i] == pattern ? 0 : 1;
+    if (bad) atomicAdd(&counts[0], bad);
+}
+
 }  // namespace
+
+cudaError_t launch_canary_fill(void* p, size_t words, unsigned pattern, int sm_count, cudaStream_t s) {
+    k_canary_fill<<<sm_count * 8, 256, 0, s>>>(static_cast<unsigned*>(p), words, pattern);
+    return cudaGetLastError();
+}
+cudaError_t launch_canary_plane(const float* plane, int w, int h, int pitch, unsigned pattern, int expect_written,
+                                unsigned long long* counts, int sm_count, cudaStream_t s) {
+    k_canary_plane<<<sm_count * 4, 256, 0, s>>>(reinterpret_cast<const unsigned*>(plane), w, h, pitch, pattern,
+                                                 expect_written, counts);
+    return cudaGetLastError();
+}
+cudaError_t launch_canary_tail(const void* p, size_t words, unsigned pattern, unsigned long long* counts, int sm_count,
+                               cudaStream_t s) {
+    k_canary_tail<<<sm_count * 4, 256, 0, s>>>(static_cast<const unsigned*>(p), words, pattern, counts);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_range(const float* px, size_t n, float* range, int sm_count, cudaStream_t s) {
     const float init[2] = {INFINITY, -INFINITY};

@@ -37,6 +37,12 @@ struct SortScratch {
     int* final_order;   // [cap_oriented]
 };
 cudaError_t launch_range(const float* px, size_t n, float* range, int sm_count, cudaStream_t s);
+// canary audit (debug): fill / verify a NaN pattern around what the scale-space kernels are allowed to write
+cudaError_t launch_canary_fill(void* p, size_t words, unsigned pattern, int sm_count, cudaStream_t s);
+cudaError_t launch_canary_plane(const float* plane, int w, int h, int pitch, unsigned pattern, int expect_written,
+                                unsigned long long* counts, int sm_count, cudaStream_t s);
+cudaError_t launch_canary_tail(const void* p, size_t words, unsigned pattern, unsigned long long* counts, int sm_count,
+                               cudaStream_t s);
 cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int border, int threshold, Cand* cands,
                            int cap, Counters* counters, int form, cudaStream_t s);
 cudaError_t launch_refine(const PyramidDesc* d_pyr, const Cand* cands, KpCore* raw,

@@ -172,6 +172,32 @@ def test_extrema_kernel_forms_find_the_same_set(ctx, shape):
     assert got.tobytes() == ref.tobytes()
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_scale_space_kernels_write_exactly_their_planes(ctx, mode):
+    """Write audit instead of a sanitizer (compute-sanitizer is closed on the GPU pool): the arena is filled with a
+    NaN pattern, then every pyramid kernel form (default mix, per-level, tile cascade, streaming cascade) must
+    overwrite every in-image element of the planes it owns and nothing else -- not the row padding, not the planes
+    that stay on chip, not the arena behind the last plane.  Sizes with ragged tiles / strips, gray and RGB,
+    doubled and not."""
+    rng = np.random.default_rng(mode)
+    shapes = [(97, 131), (192, 256), (301, 517), (64, 1030), (768, 1024), (33, 41)]
+    for h, w in shapes:
+        img = O.synth_image(max(h, 8), max(w, 8), seed=h + w)[:h, :w]
+        for doubled in (True, False):
+            for keep in (False, True):
+                ctx.debug_options(keep_all_planes=keep, unfused_pyramid=mode)
+                ctx.canary_arm()
+                k = ctx.detect(img, double_image_size=doubled)
+                stray, missing = ctx.canary_check()
+                assert (stray, missing) == (0, 0), (mode, h, w, doubled, keep, stray, missing)
+    rgb = rng.integers(0, 256, (150, 210, 3), dtype=np.uint8)
+    ctx.debug_options(unfused_pyramid=mode)
+    ctx.canary_arm()
+    ctx.detect(rgb)
+    assert ctx.canary_check() == (0, 0)
+    ctx.debug_options()
+
+
 def test_graph_replay_equals_plain_launches(ctx, synth):
     """The CUDA-graph launch plan (forked octave chain) and plain single-stream launches run the same kernels on
     the same data: identical bytes; one graph per image size / parameter set, re-captured only on a change."""
