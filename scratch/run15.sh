@@ -1,0 +1,18 @@
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -rf --maxfail=25 -p no:cacheprovider > gpurun_out/pytest_r2m.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_r2m.log
+tail -4 gpurun_out/pytest_r2m.log
+timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/b_r2m_default.json 2> gpurun_out/b_r2m_default.err
+timeout 300 python bench.py --width 7680 --height 4320 --images 32 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/b_r2m_8k.json 2> gpurun_out/b_r2m_8k.err
+timeout 300 python bench.py --width 1920 --height 1080 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/b_r2m_1080p.json 2> gpurun_out/b_r2m_1080p.err
+for f in default 8k 1080p; do python - $f <<'PY'
+import json,sys
+f=sys.argv[1]
+try:
+    d=json.loads(open('gpurun_out/b_r2m_'+f+'.json').read().strip().splitlines()[-1])
+    print(f, 'value %.1f e2e %.1f'%(d['value'],d['e2e']['value']), {k:round(v,3) for k,v in d['stages_ms'].items()}, 'sum %.3f'%sum(d['stages_ms'].values()), 'lat %.3f'%d['latency']['ms_per_image_one_stream'], 'roof %.3f'%d['roofline']['frac'], [(round(p['ms'],4),round(p['frac'],3)) for p in d['roofline']['per_kernel']], d['clocks'])
+except Exception as e:
+    print(f,'ERR',e, open('gpurun_out/b_r2m_'+f+'.err').read()[-600:])
+PY
+done
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2

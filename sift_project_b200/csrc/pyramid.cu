@@ -637,6 +637,9 @@ cudaError_t pyramid_init() {
     if ((e = cudaFuncSetAttribute(k_stream<G, SG, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamLayout<G, TM>::kSmem)) != \
         cudaSuccess)                                                                                      \
         return e;
+    SB_STREAM_ATTR(StreamA1, true, false) SB_STREAM_ATTR(StreamA1, false, false) SB_STREAM_ATTR(StreamA1, true, true) SB_STREAM_ATTR(StreamA1, false, true)
+    SB_STREAM_ATTR(StreamA2, true, false) SB_STREAM_ATTR(StreamA2, false, false) SB_STREAM_ATTR(StreamA2, true, true) SB_STREAM_ATTR(StreamA2, false, true)
+    SB_STREAM_ATTR(StreamA3, true, false) SB_STREAM_ATTR(StreamA3, false, false) SB_STREAM_ATTR(StreamA3, true, true) SB_STREAM_ATTR(StreamA3, false, true)
     SB_STREAM_ATTR(StreamA, true, true) SB_STREAM_ATTR(StreamA, false, true) SB_STREAM_ATTR(StreamB, true, true)
     SB_STREAM_ATTR(StreamB, false, true) SB_STREAM_ATTR(StreamA, true, false) SB_STREAM_ATTR(StreamA, false, false)
     SB_STREAM_ATTR(StreamB, true, false) SB_STREAM_ATTR(StreamB, false, false)
@@ -706,7 +709,19 @@ cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, floa
     a.dec = dec; a.dec_w = dec_w; a.dec_h = dec_h; a.dec_pitch = dec_pitch;
     a.w = od.w; a.h = od.h; a.pitch = od.pitch;
     a.taps[0] = taps[1]; a.taps[1] = taps[2]; a.taps[2] = taps[3];
-    if (part == 1) return stream ? launch_stream_t<StreamA>(a, sm_count, s) : launch_cascade_t<4, 5, 6>(a, sm_count, s);
+    if (part == 1) {
+        // strip geometry of the first cascade kernel: 224-column strips with two warps per level on octaves of
+        // >= 16 Mpx (less x halo, fuller warps: 7680 x 4320 in 212 us against 225 us), 96-column strips with one
+        // warp per level below (more CTAs for the smaller grids).  SIFT_B200_STREAM_A = 0 / 1 / 2 / 3 forces one
+        // (experiments; 4K batch: 731 / 743 / 743 / 711 images/s).
+        static const int forced = getenv("SIFT_B200_STREAM_A") ? atoi(getenv("SIFT_B200_STREAM_A")) : -1;
+        if (!stream) return launch_cascade_t<4, 5, 6>(a, sm_count, s);
+        const int geom = forced >= 0 ? forced : ((long long)od.w * od.h >= (16ll << 20) ? 1 : 0);
+        if (geom == 1) return launch_stream_t<StreamA1>(a, sm_count, s);
+        if (geom == 2) return launch_stream_t<StreamA2>(a, sm_count, s);
+        if (geom == 3) return launch_stream_t<StreamA3>(a, sm_count, s);
+        return launch_stream_t<StreamA>(a, sm_count, s);
+    }
     CascadeArgs b;
     b.in = od.G[3];
     b.g[0] = keep_all ? od.G[4] : nullptr; b.g[1] = keep_all ? od.G[5] : nullptr; b.g[2] = nullptr;
