@@ -410,7 +410,13 @@ k_refine(const PyramidDesc* __restrict__ pyr, const Cand* __restrict__ cands, Kp
 // Fixed-point scale: a bin can receive at most sum(w) * max|grad| <= (1 + sqrt(2 pi) s)^2 * 361
 // for pixel values in [0, 255], which is mapped to 2^32.
 // ------------------------------------------------------------------------------------------
-constexpr int ORI_COPIES = 8;
+#ifndef SB_ORI_COPIES
+#define SB_ORI_COPIES 8
+#endif
+#ifndef SB_ORI_STRIDE
+#define SB_ORI_STRIDE 36     // words between the private copies of the 36-bin histogram (copy c sits 4 c banks on)
+#endif
+constexpr int ORI_COPIES = SB_ORI_COPIES;
 constexpr int kMaxOriBins = 128;   // largest num_bins of the generic instantiation
 
 // NB > 0: compile-time bin count (36, the reference default); NB == 0: sp.num_bins at run time
@@ -425,7 +431,8 @@ k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, Kp
          Counters* __restrict__ counters, const StageParams sp) {
     constexpr int CAPB = NB > 0 ? NB : kMaxOriBins;
     constexpr int COPIES = NB > 0 ? ORI_COPIES : 2;
-    __shared__ unsigned s_hist[8][COPIES][CAPB];
+    constexpr int HSTRIDE = NB > 0 ? (SB_ORI_STRIDE >= NB ? SB_ORI_STRIDE : NB) : CAPB + 4;
+    __shared__ unsigned s_hist[8][COPIES][HSTRIDE];
     __shared__ double s_smooth[8][CAPB];
     const int nb = NB > 0 ? NB : sp.num_bins;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -455,7 +462,7 @@ k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, Kp
         const float fix = (float)(4294967296.0 / bound);
         const double unfix = bound / 4294967296.0;
         const float bins_per_rad = (float)nb * (1.0f / 6.283185307179586f);
-        for (int b = lane; b < COPIES * CAPB; b += 32) hist[b] = 0u;
+        for (int b = lane; b < COPIES * HSTRIDE; b += 32) hist[b] = 0u;
         __syncwarp();
         // window clipped to the pixels whose 4-neighbourhood is inside the image (sift.cpp:473,478)
         const int i_lo = max(-radius, 1 - x), i_hi = min(radius, W - 2 - x);
@@ -486,7 +493,7 @@ k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, Kp
         for (int b = lane; b < nb; b += 32) {
             unsigned long long t = 0;
 #pragma unroll
-            for (int cpy = 0; cpy < COPIES; ++cpy) t += hist[cpy * CAPB + b];
+            for (int cpy = 0; cpy < COPIES; ++cpy) t += hist[cpy * HSTRIDE + b];
             smooth[b] = (double)t * unfix;
         }
         __syncwarp();
@@ -694,9 +701,9 @@ __global__ void __launch_bounds__(256) k_bucket_gather(SortScratch ss) {
 // and the dense 128-byte row.
 // ------------------------------------------------------------------------------------------
 #ifndef SB_DESC_COPIES
-#define SB_DESC_COPIES 2
+#define SB_DESC_COPIES 4
 #endif
-constexpr int DESC_COPIES = SB_DESC_COPIES;   // odd / even lanes (8 copies x 4 warps measured slower: occupancy)
+constexpr int DESC_COPIES = SB_DESC_COPIES;   // one copy per lane & 3 (8 copies x 4 warps measured slower: occupancy)
 constexpr int DESC_WARPS = 8;    // warps (= keypoints in flight) per CTA
 #ifndef SB_DESC_CTAS
 #define SB_DESC_CTAS 5
@@ -705,12 +712,22 @@ constexpr int DESC_CTAS = SB_DESC_CTAS;   // CTAs per SM (the grid is exactly on
                                           // 5 (48 registers, 8 B spilled) 0.461 ms, 6 (40 registers) 0.459 ms
 constexpr int DESC_GRID = 6;                            // 4x4 cells + a one-cell border that absorbs dropped bins
 constexpr int DESC_WORDS = DESC_GRID * DESC_GRID * 8;   // per histogram copy
+// Copy stride in words.  The 32 lanes of a sample iteration are adjacent pixels: they fall into one or two cells and
+// a few orientation bins, i.e. onto 2-3 addresses.  Private copies remove the read-modify-write serialisation only
+// if they ALSO sit in different banks: 288 words is a multiple of 32, so the copies of one bin shared a bank (ncu:
+// 75 % of this kernel's shared-memory wavefronts were bank-conflict replays, and more copies did not help).  +8
+// words per copy moves copy c by 8 c banks.  Measured at 4K (ms): 2 copies, same banks 0.462; 2 copies + 4 / 8 / 16
+// words 0.376 / 0.382 / 0.385; 4 copies + 1 / 4 / 8 / 12 / 20 words 0.371 / 0.369 / 0.370 / 0.370 / 0.371.
+#ifndef SB_DESC_PAD
+#define SB_DESC_PAD 4
+#endif
+constexpr int DESC_STRIDE = DESC_WORDS + SB_DESC_PAD;
 
 __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_CTAS)
 k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ oriented,
            const int* __restrict__ final_order, Counters* __restrict__ counters,
            uint8_t* __restrict__ records, uint8_t* __restrict__ desc, int cap_final, const StageParams sp) {
-    __shared__ unsigned s_hist[DESC_WARPS][DESC_COPIES][DESC_WORDS];
+    __shared__ unsigned s_hist[DESC_WARPS][DESC_COPIES][DESC_STRIDE];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned* hist = &s_hist[warp][0][0];
@@ -738,7 +755,7 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
         const float inv_hw = (float)(1.0 / hw);
         const float pori = (float)kp.pori;
         const float fix = (float)(4294967296.0 / ((hw + 2.0) * (hw + 2.0) * mag_bound));
-        for (int b = lane; b < DESC_COPIES * DESC_WORDS; b += 32) hist[b] = 0u;
+        for (int b = lane; b < DESC_COPIES * DESC_STRIDE; b += 32) hist[b] = 0u;
         __syncwarp();
         // |col*sa + row*ca| < 2.5 hw  and  |col*ca - row*sa| < 2.5 hw  (bins in (-1, 4)), widened
         const float lim = 2.5f * (float)hw + 0.5f;
@@ -797,10 +814,55 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
                 const float dy = ldg(c - pitch) - ldg(c + pitch);
                 const float g2 = dx * dx + dy * dy;
                 const float mag = g2 > 0.f ? g2 * rsqrtf(g2) : 0.f;
-                // (Measured and reverted: floors by the magic-number round, angle wrap by compares and an integer split
-                // of the two orientation bins cut the conversion-pipe work from 18 to 8 operations per sample -- ncu had
-                // shown xu at 45 % -- but the kernel stayed at 0.462 ms and the share of bit-exact descriptors fell
-                // from 99.8 % to 99.0 %; four histogram copies instead of two: 0.469 ms.)
+#ifndef SB_DESC_DIET
+#define SB_DESC_DIET 0
+#endif
+#if SB_DESC_DIET
+                // Conversion-pipe diet -- MEASURED SLOWER, kept off (0.382 ms against 0.369 ms at 4K: the kernel is
+                // issue-bound at 77 %, and the rounded 64-bit split costs more slots than the conversions it saves).
+                // Once the histogram copies sat in different banks, the conversion / special-function pipe (16 lanes
+                // per SM) became this kernel's busiest unit (ncu: xu 59 %): 4 FRND + 11 F2I + 3 MUFU per sample.  Here
+                // the angle is wrapped with compares, the floors come
+                // from the round-to-nearest of (v - 0.5 + 1.5 * 2^23) -- floor(v) except on exact integers, where the
+                // trilinear weights make either choice the same histogram -- and the split between the two
+                // orientation bins is integer and ROUNDED (a1 = (u * fo32 + 2^31) >> 32, a0 = u - a1: exact mass, no
+                // bias; a truncating split moved 5e-6 of every sample from bin o+1 to bin o and cost 0.8 % of the
+                // bit-exact descriptors), leaving 5 F2I + 3 MUFU.
+                float ang = fast_atan2(dy, dx) - pori;  // in (-3pi, pi]
+                if (ang < 0.f) ang += 6.283185307179586f;
+                if (ang < 0.f) ang += 6.283185307179586f;
+                if (ang >= 6.283185307179586f) ang -= 6.283185307179586f;
+                const float ob = ang * (8.0f / 6.283185307179586f);
+                const float wgt = __expf(-(rr * rr + cr * cr) * 0.125f);
+                const float m = mag * wgt * fix;
+                constexpr float kMagic = 12582912.0f;          // 1.5 * 2^23, bit pattern 0x4B400000
+                const float tr = (rb - 0.5f) + kMagic, tc = (cb - 0.5f) + kMagic, to = (ob - 0.5f) + kMagic;
+                const int br = min(max(__float_as_int(tr) - 0x4B400000, -1), 4);
+                const int bc = min(max(__float_as_int(tc) - 0x4B400000, -1), 4);
+                const int bo = __float_as_int(to) - 0x4B400000;
+                const float fr = rb - (float)br, fc = cb - (float)bc;
+                const float fo = fminf(fmaxf(ob - (to - kMagic), 0.f), 1.f);
+                // trilinear spread (sift.cpp:541-571) into the 6x6 padded grid: rows / columns -1 and 4
+                // (dropped by the reference) land in the border, so no range tests are needed
+                unsigned* cell = my_hist + ((br + 1) * DESC_GRID + (bc + 1)) * 8;
+                const int o0 = bo & 7, o1 = (bo + 1) & 7;
+                const float mr0 = m * (1.0f - fr), mr1 = m * fr;
+                const unsigned u00 = __float2uint_rn(mr0 * (1.0f - fc)), u01 = __float2uint_rn(mr0 * fc);
+                const unsigned u10 = __float2uint_rn(mr1 * (1.0f - fc)), u11 = __float2uint_rn(mr1 * fc);
+                const unsigned long long fo32 = (unsigned long long)__float2uint_rn(fo * 4294967296.0f);   // saturates at 2^32 - 1
+                const unsigned a00 = (unsigned)((u00 * fo32 + 0x80000000ull) >> 32);
+                const unsigned a01 = (unsigned)((u01 * fo32 + 0x80000000ull) >> 32);
+                const unsigned a10 = (unsigned)((u10 * fo32 + 0x80000000ull) >> 32);
+                const unsigned a11 = (unsigned)((u11 * fo32 + 0x80000000ull) >> 32);
+                atomicAdd(cell + o0, u00 - a00);
+                atomicAdd(cell + o1, a00);
+                atomicAdd(cell + 8 + o0, u01 - a01);
+                atomicAdd(cell + 8 + o1, a01);
+                atomicAdd(cell + DESC_GRID * 8 + o0, u10 - a10);
+                atomicAdd(cell + DESC_GRID * 8 + o1, a10);
+                atomicAdd(cell + DESC_GRID * 8 + 8 + o0, u11 - a11);
+                atomicAdd(cell + DESC_GRID * 8 + 8 + o1, a11);
+#else
                 float ang = fast_atan2(dy, dx) - pori;  // in (-3pi, pi]
                 ang -= 6.283185307179586f * floorf(ang * (1.0f / 6.283185307179586f));
                 if (ang < 0.f) ang = 0.f;
@@ -826,6 +888,7 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
                 atomicAdd(cell + DESC_GRID * 8 + o1, __float2uint_rn(v10 * fo));
                 atomicAdd(cell + DESC_GRID * 8 + 8 + o0, __float2uint_rn(v11 * w0));
                 atomicAdd(cell + DESC_GRID * 8 + 8 + o1, __float2uint_rn(v11 * fo));
+#endif
             }
         }
         __syncwarp();
@@ -838,7 +901,7 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
             // bin 4L+k = (row L/8, column (L/2)%4, orientation 4(L%2)+k) of the inner 4x4 cells
             const int cellw = (((lane >> 3) + 1) * DESC_GRID + ((lane >> 1) & 3) + 1) * 8 + 4 * (lane & 1) + k;
 #pragma unroll
-            for (int cpy = 0; cpy < DESC_COPIES; ++cpy) t += hist[cpy * DESC_WORDS + cellw];
+            for (int cpy = 0; cpy < DESC_COPIES; ++cpy) t += hist[cpy * DESC_STRIDE + cellw];
             hv[k] = (double)t;
             ss += hv[k] * hv[k];
         }
