@@ -1013,7 +1013,8 @@ cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int bord
     const long long px = (long long)oct.w * oct.h;
     if (form != 1) {   // form 1: the one-column-per-lane kernel (kept for comparison; same candidate set)
         // rows per warp: long walks on large octaves (2 halo rows each), short ones where the grid would not fill the GPU
-        const int rows = px >= (16ll << 20) ? 32 : px >= (1ll << 20) ? 16 : px >= (1ll << 16) ? 4 : 2;
+        static const int rows_mid = getenv("SIFT_B200_EX_ROWS_MID") ? atoi(getenv("SIFT_B200_EX_ROWS_MID")) : 16;   // experiments
+        const int rows = px >= (16ll << 20) ? 32 : px >= (1ll << 20) ? rows_mid : px >= (1ll << 16) ? 4 : 2;
         dim3 grid(oct.w / EX4_STRIP + 1, (oct.h - 2 + 4 * rows - 1) / (4 * rows));
         const int strips = oct.w / EX4_STRIP + 1;
         const dim3 grid_x((strips + 3) / 4, (oct.h - 2 + rows - 1) / rows);   // XW = 4: warps side by side

@@ -334,10 +334,13 @@ k_match_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                                 const int* u = w + 8 * g;
                                 const int4 c0 = *reinterpret_cast<const int4*>(cp + ch * 16 + 8 * g);
                                 const int4 c1 = *reinterpret_cast<const int4*>(cp + ch * 16 + 8 * g + 4);
-                                const int k0 = u[0] * -512 + c0.x, k1 = u[1] * -512 + c0.y;
-                                const int k2 = u[2] * -512 + c0.z, k3 = u[3] * -512 + c0.w;
-                                const int k4 = u[4] * -512 + c1.x, k5 = u[5] * -512 + c1.y;
-                                const int k6 = u[6] * -512 + c1.z, k7 = u[7] * -512 + c1.w;
+                                // key = c' - 512 dot: the product alone reaches 4.3e9, so it is formed in unsigned
+                                // arithmetic (defined wrap-around); the key itself is below 2^31
+                                auto key = [](int dot, int c) { return (int)((unsigned)c - ((unsigned)dot << 9)); };
+                                const int k0 = key(u[0], c0.x), k1 = key(u[1], c0.y);
+                                const int k2 = key(u[2], c0.z), k3 = key(u[3], c0.w);
+                                const int k4 = key(u[4], c1.x), k5 = key(u[5], c1.y);
+                                const int k6 = key(u[6], c1.z), k7 = key(u[7], c1.w);
                                 // tournament: the two smallest of the eight keys (short dependency chains) ...
                                 int a1, a2, b1, b2, lo, hi;
                                 merge2(min(k0, k1), max(k0, k1), min(k2, k3), max(k2, k3), a1, a2);

@@ -640,6 +640,7 @@ cudaError_t pyramid_init() {
     SB_STREAM_ATTR(StreamA1, true, false) SB_STREAM_ATTR(StreamA1, false, false) SB_STREAM_ATTR(StreamA1, true, true) SB_STREAM_ATTR(StreamA1, false, true)
     SB_STREAM_ATTR(StreamA2, true, false) SB_STREAM_ATTR(StreamA2, false, false) SB_STREAM_ATTR(StreamA2, true, true) SB_STREAM_ATTR(StreamA2, false, true)
     SB_STREAM_ATTR(StreamA3, true, false) SB_STREAM_ATTR(StreamA3, false, false) SB_STREAM_ATTR(StreamA3, true, true) SB_STREAM_ATTR(StreamA3, false, true)
+    SB_STREAM_ATTR(StreamBn, true, false) SB_STREAM_ATTR(StreamBn, false, false) SB_STREAM_ATTR(StreamBn, true, true) SB_STREAM_ATTR(StreamBn, false, true)
     SB_STREAM_ATTR(StreamA, true, true) SB_STREAM_ATTR(StreamA, false, true) SB_STREAM_ATTR(StreamB, true, true)
     SB_STREAM_ATTR(StreamB, false, true) SB_STREAM_ATTR(StreamA, true, false) SB_STREAM_ATTR(StreamA, false, false)
     SB_STREAM_ATTR(StreamB, true, false) SB_STREAM_ATTR(StreamB, false, false)
@@ -729,7 +730,11 @@ cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, floa
     b.dec = nullptr; b.dec_w = b.dec_h = b.dec_pitch = 0;
     b.w = od.w; b.h = od.h; b.pitch = od.pitch;
     b.taps[0] = taps[4]; b.taps[1] = taps[5]; b.taps[2] = taps[5];
-    return stream ? launch_stream_t<StreamB>(b, sm_count, s) : launch_cascade_t<8, 10, 0>(b, sm_count, s);
+    if (!stream) return launch_cascade_t<8, 10, 0>(b, sm_count, s);
+    // SIFT_B200_STREAM_B_NARROW_PX: octaves below this many pixels take the narrow geometry (experiments; default 0 = never)
+    static const long long narrow_px = getenv("SIFT_B200_STREAM_B_NARROW_PX") ? atoll(getenv("SIFT_B200_STREAM_B_NARROW_PX")) : 0;
+    if ((long long)od.w * od.h < narrow_px) return launch_stream_t<StreamBn>(b, sm_count, s);
+    return launch_stream_t<StreamB>(b, sm_count, s);
 }
 
 cudaError_t launch_prepare_u8(const uint8_t* src, int sw, int sh, int ch, float* dst, int dw, int dh,

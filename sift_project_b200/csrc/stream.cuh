@@ -536,6 +536,8 @@ using StreamA = StreamGeom<3, 4, 5, 6, 4, 96, 12, 5, true, 1>;    // G0 -> G1,G2
 // last warps -- at fewer resident warps: used on octaves of >= 16 Mpx (A1); A2 / A3: experiments
 using StreamA1 = StreamGeom<3, 4, 5, 6, 4, 224, 12, 2, true, 1>;
 using StreamA2 = StreamGeom<3, 4, 5, 6, 4, 224, 12, 3, true, 1>;
+// narrow second-kernel geometry (one warp per level) for octaves whose 232-column strips do not fill the GPU
+using StreamBn = StreamGeom<2, 8, 10, 0, 4, 104, 6, 6, true, 2>;
 using StreamA3 = StreamGeom<3, 4, 5, 6, 4, 160, 12, 3, true, 1>;
 using StreamB = StreamGeom<2, 8, 10, 0, 4, 232, 6, 3, true, 2>;   // G3 -> (G4,G5) -> D3,D4
 
