@@ -1,5 +1,6 @@
-// Development harness (not shipped): streaming cascade (stream.cuh) vs the tile cascade (k_cascade):
-// bitwise comparison on a set of image sizes, then timing at the 4K / 1080p octave-0 sizes.
+// Development harness (not shipped): streaming cascade (stream.cuh, cp.async input form) vs the tile cascade (k_cascade):
+// bitwise comparison on a set of image sizes, then timing at the 4K / 1080p octave-0 sizes.  Call pyramid_init() first
+// when the TMA form is wanted (it resolves cuTensorMapEncodeTiled).
 #ifndef PYR_SRC
 #define PYR_SRC "../sift_project_b200/csrc/pyramid.cu"
 #endif
@@ -92,10 +93,10 @@ static int check(int w, int h, int segs, bool onewarp) {
 
 template <class GA, class GB>
 static void time_variant(const char* name, Planes& p, int w, int h, int pitch, int segs) {
-    cudaFuncSetAttribute(k_stream<GA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GA::kSmem);
-    cudaFuncSetAttribute(k_stream<GB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB::kSmem);
-    cudaFuncSetAttribute(k_stream<GA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GA::kSmem);
-    cudaFuncSetAttribute(k_stream<GB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB::kSmem);
+    cudaFuncSetAttribute(k_stream<GA, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamLayout<GA, false>::kSmem);
+    cudaFuncSetAttribute(k_stream<GB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamLayout<GB, false>::kSmem);
+    cudaFuncSetAttribute(k_stream<GA, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamLayout<GA, false>::kSmem);
+    cudaFuncSetAttribute(k_stream<GB, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamLayout<GB, false>::kSmem);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best[2] = {1e9f, 1e9f};
     for (int variant = 0; variant < 2; ++variant) {
@@ -110,10 +111,10 @@ static void time_variant(const char* name, Planes& p, int w, int h, int pitch, i
         }
     }
     int occA = 0, occB = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, k_stream<GA, true>, GA::THREADS, GA::kSmem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, k_stream<GB, false>, GB::THREADS, GB::kSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, k_stream<GA, true, false>, GA::THREADS, StreamLayout<GA, false>::kSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, k_stream<GB, false, false>, GB::THREADS, StreamLayout<GB, false>::kSmem);
     printf("  %-34s segs %2d: A %7.1f us  B %7.1f us  sum %7.1f us  (CTAs/SM %d / %d, smem %zu / %zu)\n", name, segs,
-           best[0] * 1e3, best[1] * 1e3, (best[0] + best[1]) * 1e3, occA, occB, GA::kSmem, GB::kSmem);
+           best[0] * 1e3, best[1] * 1e3, (best[0] + best[1]) * 1e3, occA, occB, StreamLayout<GA, false>::kSmem, StreamLayout<GB, false>::kSmem);
 }
 
 static void time_size(int w, int h) {
@@ -173,8 +174,8 @@ int run(int argc, char** argv) {
     {
         using CA = StreamGeom<3, 4, 5, 6, 2, 96, 12, 4, true, 1>;
         using CB = StreamGeom<2, 8, 10, 0, 2, 104, 6, 5, true, 2>;
-        cudaFuncSetAttribute(k_stream<CA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CA::kSmem);
-        cudaFuncSetAttribute(k_stream<CB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB::kSmem);
+        cudaFuncSetAttribute(k_stream<CA, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamLayout<CA, false>::kSmem);
+        cudaFuncSetAttribute(k_stream<CB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamLayout<CB, false>::kSmem);
     }
     if (argc > 1 && !strcmp(argv[1], "prof")) {
         const int w = 7680, h = 4320, pitch = 7680;
