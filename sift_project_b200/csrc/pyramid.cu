@@ -638,9 +638,6 @@ cudaError_t pyramid_init() {
         cudaSuccess)                                                                                      \
         return e;
     SB_STREAM_ATTR(StreamA1, true, false) SB_STREAM_ATTR(StreamA1, false, false) SB_STREAM_ATTR(StreamA1, true, true) SB_STREAM_ATTR(StreamA1, false, true)
-    SB_STREAM_ATTR(StreamA2, true, false) SB_STREAM_ATTR(StreamA2, false, false) SB_STREAM_ATTR(StreamA2, true, true) SB_STREAM_ATTR(StreamA2, false, true)
-    SB_STREAM_ATTR(StreamA3, true, false) SB_STREAM_ATTR(StreamA3, false, false) SB_STREAM_ATTR(StreamA3, true, true) SB_STREAM_ATTR(StreamA3, false, true)
-    SB_STREAM_ATTR(StreamBn, true, false) SB_STREAM_ATTR(StreamBn, false, false) SB_STREAM_ATTR(StreamBn, true, true) SB_STREAM_ATTR(StreamBn, false, true)
     SB_STREAM_ATTR(StreamA, true, true) SB_STREAM_ATTR(StreamA, false, true) SB_STREAM_ATTR(StreamB, true, true)
     SB_STREAM_ATTR(StreamB, false, true) SB_STREAM_ATTR(StreamA, true, false) SB_STREAM_ATTR(StreamA, false, false)
     SB_STREAM_ATTR(StreamB, true, false) SB_STREAM_ATTR(StreamB, false, false)
@@ -713,14 +710,11 @@ cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, floa
     if (part == 1) {
         // strip geometry of the first cascade kernel: 224-column strips with two warps per level on octaves of
         // >= 16 Mpx (less x halo, fuller warps: 7680 x 4320 in 212 us against 225 us), 96-column strips with one
-        // warp per level below (more CTAs for the smaller grids).  SIFT_B200_STREAM_A = 0 / 1 / 2 / 3 forces one
-        // (experiments; 4K batch: 731 / 743 / 743 / 711 images/s).
+        // warp per level below (more CTAs for the smaller grids).  SIFT_B200_STREAM_A = 0 / 1 forces one of them.
         static const int forced = getenv("SIFT_B200_STREAM_A") ? atoi(getenv("SIFT_B200_STREAM_A")) : -1;
         if (!stream) return launch_cascade_t<4, 5, 6>(a, sm_count, s);
         const int geom = forced >= 0 ? forced : ((long long)od.w * od.h >= (16ll << 20) ? 1 : 0);
         if (geom == 1) return launch_stream_t<StreamA1>(a, sm_count, s);
-        if (geom == 2) return launch_stream_t<StreamA2>(a, sm_count, s);
-        if (geom == 3) return launch_stream_t<StreamA3>(a, sm_count, s);
         return launch_stream_t<StreamA>(a, sm_count, s);
     }
     CascadeArgs b;
@@ -731,9 +725,6 @@ cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, floa
     b.w = od.w; b.h = od.h; b.pitch = od.pitch;
     b.taps[0] = taps[4]; b.taps[1] = taps[5]; b.taps[2] = taps[5];
     if (!stream) return launch_cascade_t<8, 10, 0>(b, sm_count, s);
-    // SIFT_B200_STREAM_B_NARROW_PX: octaves below this many pixels take the narrow geometry (experiments; default 0 = never)
-    static const long long narrow_px = getenv("SIFT_B200_STREAM_B_NARROW_PX") ? atoll(getenv("SIFT_B200_STREAM_B_NARROW_PX")) : 0;
-    if ((long long)od.w * od.h < narrow_px) return launch_stream_t<StreamBn>(b, sm_count, s);
     return launch_stream_t<StreamB>(b, sm_count, s);
 }
 

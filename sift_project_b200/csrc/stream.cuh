@@ -533,12 +533,11 @@ k_stream(const CascadeArgs a, const __grid_constant__ CUtensorMap tmap, const in
 // two independent rows in the horizontal pass), 3 CTAs per SM.  Measured alternatives in DESIGN.md.
 using StreamA = StreamGeom<3, 4, 5, 6, 4, 96, 12, 5, true, 1>;    // G0 -> G1,G2,G3, D0,D1,D2, next base
 // wider strips with two warps per level -- less x halo (level 1 computes 1.14x instead of 1.33x the strip), fuller
-// last warps -- at fewer resident warps: used on octaves of >= 16 Mpx (A1); A2 / A3: experiments
+// last warps -- at fewer resident warps: used on octaves of >= 16 Mpx.  Measured and not instantiated any more (4K
+// batch images/s, the geometry forced on every streaming octave): <.., 224, 12, 3 CTAs/SM> 743 (same as A1),
+// <.., 160, 12, 3> 711 (half-empty second warps) against 731 for A everywhere and 743 for A1 everywhere; a narrow
+// second kernel <2, 8, 10, 0, 4, 104, 6, 6, true, 2> on octaves below 3 / 10 Mpx: 797 / 795 against 802.
 using StreamA1 = StreamGeom<3, 4, 5, 6, 4, 224, 12, 2, true, 1>;
-using StreamA2 = StreamGeom<3, 4, 5, 6, 4, 224, 12, 3, true, 1>;
-// narrow second-kernel geometry (one warp per level) for octaves whose 232-column strips do not fill the GPU
-using StreamBn = StreamGeom<2, 8, 10, 0, 4, 104, 6, 6, true, 2>;
-using StreamA3 = StreamGeom<3, 4, 5, 6, 4, 160, 12, 3, true, 1>;
 using StreamB = StreamGeom<2, 8, 10, 0, 4, 232, 6, 3, true, 2>;   // G3 -> (G4,G5) -> D3,D4
 
 // 2-D tensor map of one FP32 plane (w x h, `pitch` floats per row) with a BOXW x 1 box, no swizzle, zero fill
