@@ -703,6 +703,43 @@ def test_batch_detect_over_several_contexts(synth):
         c.close()
 
 
+def test_contexts_come_and_go_without_leaking_and_sizes_may_alternate():
+    """Housekeeping of the host layer: contexts created and destroyed in a loop give the device memory back (arena,
+    lists, graph, streams, events); one context fed alternating image sizes and parameters re-captures its graph and
+    keeps returning the bytes a fresh context returns; several contexts interleaved on one GPU do not disturb each
+    other."""
+    import torch
+    imgs = [O.synth_image(120, 160, seed=1), O.synth_image(200, 150, seed=2), O.synth_image(96, 300, seed=3)]
+    with S.SiftContext(320, 240) as c:
+        want = [c.detect(im) for im in imgs]
+        want_p = c.detect(imgs[0], peak_ratio=0.7)
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for rep in range(12):
+        with S.SiftContext(320, 240) as c:
+            for k in (0, 1, 0, 2, 1):
+                assert c.detect(imgs[k]).tobytes() == want[k].tobytes(), (rep, k)
+            assert c.detect(imgs[0], peak_ratio=0.7).tobytes() == want_p.tobytes()
+            assert c.detect(imgs[0]).tobytes() == want[0].tobytes()
+            a, b = O.synth_descriptors(400, seed=rep), O.synth_descriptors(900, seed=rep + 50)
+            c.match(a, b)
+            c.collection_match(2, [a, b])
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 64 << 20, (free0, free1)      # nothing accumulates (allocator granularity aside)
+    ctxs = [S.SiftContext(320, 240) for _ in range(4)]
+    for rep in range(3):
+        for k, c in enumerate(ctxs):
+            c.detect_enqueue(np.ascontiguousarray(imgs[(k + rep) % 3]), imgs[(k + rep) % 3].shape[1], imgs[(k + rep) % 3].shape[0])
+        for k, c in enumerate(ctxs):
+            n = c.detect_finish()
+            out = np.zeros(n, dtype=S.KP_DTYPE)
+            assert c.result_copy(out) == n
+            assert out.tobytes() == want[(k + rep) % 3].tobytes()
+    for c in ctxs:
+        c.close()
+
+
 def test_match_self_is_identity(ctx):
     """match(A, A): every row's nearest neighbour is itself at distance 0 (any size, both kernels)."""
     import torch
