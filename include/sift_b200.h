@@ -246,6 +246,10 @@ int sift_b200_debug_canary_check(sift_b200_ctx* ctx, int64_t* stray_writes, int6
  * finer; every consumer takes differences, so results change only by less rounding.  extrema_form (default 0;
  * env SIFT_B200_EXTREMA): 0 = the four-columns-per-lane extrema kernel, 1 = the one-column form (same set). */
 int sift_b200_debug_launch_plan(sift_b200_ctx* ctx, int use_graph, int centred, int extrema_form);
+/* one_launch = 1 (default; env SIFT_B200_TAIL): the octaves of at most one 32 x 32 tile per SM -- seven of the ten
+ * octaves of a 4K image, latency-bound one by one -- run their cascades in ONE ticket-ordered launch and their extrema
+ * scans in another; 0 = two cascade launches + one scan per octave as for the large octaves.  Same bytes. */
+int sift_b200_debug_tail(sift_b200_ctx* ctx, int one_launch);
 /* how many CUDA graphs this context has captured so far (one per distinct image size / parameter set in a row) */
 long sift_b200_graphs_built(const sift_b200_ctx* ctx);
 /* number of kernel launches issued by this context since creation (bench's gpu_launches) */

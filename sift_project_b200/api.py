@@ -116,6 +116,7 @@ def load_library():
         "sift_b200_debug_orient": (i32, [vp, vp, i32, vp, i32, i32p]),
         "sift_b200_debug_describe": (i32, [vp, vp, i32]),
         "sift_b200_debug_launch_plan": (i32, [vp, i32, i32, i32]),
+        "sift_b200_debug_tail": (i32, [vp, i32]),
         "sift_b200_debug_canary_arm": (i32, [vp]),
         "sift_b200_debug_canary_check": (i32, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         "sift_b200_result_copy": (i32, [vp, vp, i32, i32p]),
@@ -386,6 +387,10 @@ class SiftContext:
         self._check(self._L.sift_b200_debug_launch_plan(self._h, -1 if use_graph is None else int(use_graph),
                                                         -1 if centred is None else int(centred),
                                                         -1 if extrema_form is None else int(extrema_form)))
+
+    def tail_kernel(self, one_launch=True):
+        """The small octaves in one cascade launch + one extrema launch (default) or octave by octave."""
+        self._check(self._L.sift_b200_debug_tail(self._h, int(bool(one_launch))))
 
     def canary_arm(self):
         self._check(self._L.sift_b200_debug_canary_arm(self._h))

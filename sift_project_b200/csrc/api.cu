@@ -73,6 +73,7 @@ struct sift_b200_ctx {
     // extrema scan of each octave on a side stream, so the small octaves overlap the large ones ----
     bool use_graph = true;
     bool three_branches = false; // experiments (SIFT_B200_GRAPH=3): extrema scans on a third graph branch
+    bool use_tail = true;        // the latency-bound small octaves in one launch (k_tail); SIFT_B200_TAIL=0: one by one
     long long fork_min_px = 300000;   // octaves of at least this many pixels run their second half on the side branch
     int extrema_form = 0;        // 0 = four columns per lane (default), 1 = one column per lane
     cudaStream_t side = nullptr, side2 = nullptr;
@@ -270,6 +271,7 @@ struct DetectPlan {
     bool fused;
     BlurTaps taps[kMaxLayers];
 };
+constexpr size_t kCountersBytes = sizeof(Counters) + (2 + kMaxOctaves) * sizeof(int);
 
 int enqueue_body(sift_b200_ctx* c, const DetectPlan& pl, bool forked, int* n_launches, int* stage_launches) {
     const StageParams& sp = c->sp;
@@ -288,8 +290,33 @@ int enqueue_body(sift_b200_ctx* c, const DetectPlan& pl, bool forked, int* n_lau
         if (stage_launches) stage_launches[stage] += launches;
         if (!forked) prof_mark(c, stage, 0);
     };
+    // the tail: the run of last octaves that are at most one 32 x 32 tile per SM each -- one launch for their
+    // cascades, one for their extrema scans (default plan only: the kernel-form switches keep one launch per octave,
+    // which is also what the tests compare the tail against)
+    int tail_first = pl.octaves;
+    if (pl.fused && c->use_tail && c->fused_mode == 0) {
+        while (tail_first > 0 && tail_eligible(c->pyr.oct[tail_first - 1], c->sm_count)) --tail_first;
+        if (pl.octaves - tail_first < 2 || pl.octaves - tail_first > 12) tail_first = pl.octaves;
+    }
     for (int o = 0; o < pl.octaves; ++o) {
         OctaveDesc& od = c->pyr.oct[o];
+        if (o == tail_first) {
+            const int n = pl.octaves - o;
+            CU(c, launch_tail(c->pyr.oct, o, pl.octaves, pl.taps, c->keep_planes, (int*)(c->d_counters + 1), c->sm_count, s));
+            mark(SIFT_B200_STAGE_PYRAMID, 1);
+            if (extrema_multi_supported(sp.border, c->extrema_form)) {
+                CU(c, launch_extrema_multi(c->pyr.oct, o, n, pl.dogs, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, s));
+                mark(SIFT_B200_STAGE_EXTREMA, 1);
+            } else {
+                for (int q = o; q < pl.octaves; ++q) {
+                    const OctaveDesc& oq = c->pyr.oct[q];
+                    if (oq.w < 2 * sp.border + 1 || oq.h < 2 * sp.border + 1) continue;
+                    CU(c, launch_extrema(oq, q, pl.dogs, sp.border, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, c->extrema_form, s));
+                    mark(SIFT_B200_STAGE_EXTREMA, 1);
+                }
+            }
+            break;
+        }
         const bool on_side = forked && (long long)od.w * od.h >= c->fork_min_px;
         cudaStream_t s2 = on_side ? c->side : s, s3 = (three && on_side) ? c->side2 : s2;
         float* dec = nullptr;
@@ -385,7 +412,7 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
         memcpy(&c->pyr_uploaded, &c->pyr, sizeof(PyramidDesc));
         c->pyr_uploaded_valid = true;
     }
-    CU(c, cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), s));
+    CU(c, cudaMemsetAsync(c->d_counters, 0, kCountersBytes, s));
 
     StageParams& sp = c->sp;
     memset(&sp, 0, sizeof sp);   // (it is part of the graph key: no indeterminate padding)
@@ -476,8 +503,8 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     std::vector<uint8_t> key;
     auto put = [&](const void* q, size_t n) { key.insert(key.end(), (const uint8_t*)q, (const uint8_t*)q + n); };
     put(&pl, sizeof pl); put(&sp, sizeof sp); put(&c->pyr, sizeof c->pyr); put(&c->ss.nb, sizeof(int));
-    const int dbg[6] = {c->keep_planes, c->force_unfused, c->fused_mode, c->extrema_form, c->three_branches,
-                        (int)std::min<long long>(c->fork_min_px, 1ll << 30)};
+    const int dbg[7] = {c->keep_planes, c->force_unfused, c->fused_mode, c->extrema_form, c->three_branches,
+                        (int)std::min<long long>(c->fork_min_px, 1ll << 30), c->use_tail};
     put(dbg, sizeof dbg);
     if (!c->graph_exec || key != c->graph_key) {
         if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
@@ -619,6 +646,7 @@ int sift_b200_create(int device, int max_width, int max_height, sift_b200_ctx** 
     if (const char* m = getenv("SIFT_B200_GRAPH")) { c->use_graph = atoi(m) != 0; c->three_branches = atoi(m) == 3; }
     if (const char* m = getenv("SIFT_B200_EXTREMA")) c->extrema_form = atoi(m);
     if (const char* m = getenv("SIFT_B200_FORK_MIN_PX")) c->fork_min_px = atoll(m);
+    if (const char* m = getenv("SIFT_B200_TAIL")) c->use_tail = atoi(m) != 0;
     c->max_w = max_width;
     c->max_h = max_height;
 #define CRT(call)                                                                                   \
@@ -646,7 +674,7 @@ int sift_b200_create(int device, int max_width, int max_height, sift_b200_ctx** 
     c->input_bytes = (size_t)max_width * max_height * 3 * sizeof(float);
     CRT(cudaMalloc(&c->d_input, c->input_bytes));
     CRT(cudaMalloc(&c->d_pyr, sizeof(PyramidDesc)));
-    CRT(cudaMalloc(&c->d_counters, sizeof(Counters)));
+    CRT(cudaMalloc(&c->d_counters, kCountersBytes));   // the counters + k_tail's ticket / hand-over counters
     CRT(cudaMalloc(&c->d_range, 2 * sizeof(float)));
     CRT(cudaMallocHost(&c->h_counters, sizeof(Counters)));
     const size_t px = (size_t)max_width * max_height;
@@ -1142,6 +1170,12 @@ int sift_b200_debug_launch_plan(sift_b200_ctx* c, int use_graph, int centred, in
     if (use_graph >= 0) c->use_graph = use_graph != 0;
     if (centred >= 0) c->centred = centred != 0;
     if (extrema_form >= 0) c->extrema_form = extrema_form;
+    return SIFT_B200_OK;
+}
+
+int sift_b200_debug_tail(sift_b200_ctx* c, int one_launch) {
+    if (!c) return SIFT_B200_E_INVALID;
+    c->use_tail = one_launch != 0;
     return SIFT_B200_OK;
 }
 

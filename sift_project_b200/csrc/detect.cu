@@ -186,18 +186,18 @@ constexpr int EX4_STRIP = 124;   // tested columns per warp: 128 loaded minus 2 
 // SLOTS = rows of the rotating register window (3 in use + SLOTS - 3 in flight), CTAS = CTAs per SM
 // XW = 1: the 4 warps of a CTA take consecutive row bands of one strip; XW = 4: they take 4 adjacent strips of one
 // row band and walk down side by side, so that a CTA reads ~2 KB contiguous per plane row (DRAM pages)
-template <int ND, int SLOTS, int CTAS, int XW>
-__global__ void __launch_bounds__(128, CTAS)
-k_extrema4(const OctaveDesc oct, int octave, float thr, int rows, Cand* __restrict__ cands, int cap,
-           Counters* __restrict__ counters) {
+template <int ND, int SLOTS, int XW>
+__device__ __forceinline__ void extrema4_body(const OctaveDesc& oct, int octave, float thr, int rows,
+                                              Cand* __restrict__ cands, int cap, Counters* __restrict__ counters,
+                                              int bx, int by) {
     constexpr int NZ = ND - 2;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w = oct.w, h = oct.h, pitch = oct.pitch;
-    const int strip = XW == 4 ? blockIdx.x * 4 + warp : blockIdx.x;
+    const int strip = XW == 4 ? bx * 4 + warp : bx;
     if (strip * EX4_STRIP - 2 > w - 2) return;          // (XW = 4) a strip beyond the last tested column
     const int x0 = strip * EX4_STRIP - 4 + 4 * lane;    // this lane's first column; the strip tests lane positions 2..125
-    const int ys = 1 + (XW == 4 ? blockIdx.y : blockIdx.y * 4 + warp) * rows;      // first tested row of this warp
+    const int ys = 1 + (XW == 4 ? by : by * 4 + warp) * rows;      // first tested row of this warp
     if (ys > h - 2) return;
     const int ye = min(ys + rows - 1, h - 2);
     // lanes hanging over the left / right end of the row load a clamped (wrong, unused) position: their columns are
@@ -280,6 +280,36 @@ k_extrema4(const OctaveDesc oct, int octave, float thr, int rows, Cand* __restri
             test_row(win[j % SLOTS], win[(j + 1) % SLOTS], win[(j + 2) % SLOTS], y);
         }
     }
+}
+
+template <int ND, int SLOTS, int CTAS, int XW>
+__global__ void __launch_bounds__(128, CTAS)
+k_extrema4(const OctaveDesc oct, int octave, float thr, int rows, Cand* __restrict__ cands, int cap,
+           Counters* __restrict__ counters) {
+    extrema4_body<ND, SLOTS, XW>(oct, octave, thr, rows, cands, cap, counters, blockIdx.x, blockIdx.y);
+}
+
+// The scans of the small octaves (the ones k_tail produced) in one launch: a CTA finds its octave in a prefix table
+// and runs the same body.  Six launches of 5-9 us, each a single partial wave, become one.
+constexpr int kMaxExtremaMulti = 12;
+struct ExtremaMulti {
+    int n;
+    int cta_begin[kMaxExtremaMulti + 1];
+    int gx[kMaxExtremaMulti], rows[kMaxExtremaMulti], octave[kMaxExtremaMulti];
+    OctaveDesc oct[kMaxExtremaMulti];
+};
+template <int ND>
+__global__ void __launch_bounds__(128, 3)
+k_extrema4_multi(const ExtremaMulti m, float thr, Cand* __restrict__ cands, int cap, Counters* __restrict__ counters) {
+    int i = 0;
+    while ((int)blockIdx.x >= m.cta_begin[i + 1]) ++i;
+    const int k = blockIdx.x - m.cta_begin[i];
+    const int gx = m.gx[i];
+    OctaveDesc od;
+    od.w = m.oct[i].w; od.h = m.oct[i].h; od.pitch = m.oct[i].pitch;
+#pragma unroll
+    for (int z = 0; z < ND; ++z) od.D[z] = m.oct[i].D[z];
+    extrema4_body<ND, 4, 4>(od, m.octave[i], thr, m.rows[i], cands, cap, counters, k % gx, k / gx);
 }
 
 // Generic window (window_size = 5, 7: border = 2, 3): the same tie-tolerant test over the
@@ -1002,6 +1032,8 @@ cudaError_t launch_range(const float* px, size_t n, float* range, int sm_count, 
     return cudaGetLastError();
 }
 
+static int extrema4_rows(long long px);
+
 cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int border, int threshold, Cand* cands,
                            int cap, Counters* counters, int form, cudaStream_t s) {
     if (oct.w < 2 * border + 1 || oct.h < 2 * border + 1) return cudaSuccess;
@@ -1013,8 +1045,7 @@ cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int bord
     const long long px = (long long)oct.w * oct.h;
     if (form != 1) {   // form 1: the one-column-per-lane kernel (kept for comparison; same candidate set)
         // rows per warp: long walks on large octaves (2 halo rows each), short ones where the grid would not fill the GPU
-        static const int rows_mid = getenv("SIFT_B200_EX_ROWS_MID") ? atoi(getenv("SIFT_B200_EX_ROWS_MID")) : 16;   // experiments
-        const int rows = px >= (16ll << 20) ? 32 : px >= (1ll << 20) ? rows_mid : px >= (1ll << 16) ? 4 : 2;
+        const int rows = extrema4_rows(px);
         dim3 grid(oct.w / EX4_STRIP + 1, (oct.h - 2 + 4 * rows - 1) / (4 * rows));
         const int strips = oct.w / EX4_STRIP + 1;
         const dim3 grid_x((strips + 3) / 4, (oct.h - 2 + rows - 1) / rows);   // XW = 4: warps side by side
@@ -1050,6 +1081,47 @@ cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int bord
         default: return cudaErrorInvalidValue;
     }
 #undef SB_EX
+    return cudaGetLastError();
+}
+
+// rows per warp of the four-column scan: long walks on large octaves (2 halo rows each), short ones where the grid
+// would not fill the GPU
+static int extrema4_rows(long long px) {
+    static const int rows_mid = getenv("SIFT_B200_EX_ROWS_MID") ? atoi(getenv("SIFT_B200_EX_ROWS_MID")) : 16;   // experiments
+    return px >= (16ll << 20) ? 32 : px >= (1ll << 20) ? rows_mid : px >= (1ll << 16) ? 4 : 2;
+}
+
+bool extrema_multi_supported(int border, int form) { return border == 1 && form != 1 && form != 2; }
+
+// octaves first .. first + n - 1 in one launch (window 3 only); same candidate set as n launch_extrema calls
+cudaError_t launch_extrema_multi(const OctaveDesc* octs, int first, int n, int dogs, int threshold, Cand* cands, int cap,
+                                 Counters* counters, cudaStream_t s) {
+    if (n > kMaxExtremaMulti) return cudaErrorInvalidValue;
+    ExtremaMulti m;
+    memset(&m, 0, sizeof m);
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+        const OctaveDesc& od = octs[first + i];
+        if (od.w < 3 || od.h < 3) continue;
+        const int j = m.n++;
+        const int rows = extrema4_rows((long long)od.w * od.h);
+        const int strips = od.w / EX4_STRIP + 1;
+        m.gx[j] = (strips + 3) / 4;
+        m.rows[j] = rows;
+        m.octave[j] = first + i;
+        m.oct[j] = od;
+        m.cta_begin[j] = total;
+        total += m.gx[j] * ((od.h - 2 + rows - 1) / rows);
+    }
+    m.cta_begin[m.n] = total;
+    if (total == 0) return cudaSuccess;
+    switch (dogs) {
+        case 4: k_extrema4_multi<4><<<total, 128, 0, s>>>(m, (float)threshold, cands, cap, counters); break;
+        case 5: k_extrema4_multi<5><<<total, 128, 0, s>>>(m, (float)threshold, cands, cap, counters); break;
+        case 6: k_extrema4_multi<6><<<total, 128, 0, s>>>(m, (float)threshold, cands, cap, counters); break;
+        case 7: k_extrema4_multi<7><<<total, 128, 0, s>>>(m, (float)threshold, cands, cap, counters); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

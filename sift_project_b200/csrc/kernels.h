@@ -22,6 +22,10 @@ cudaError_t launch_input_u8(const uint8_t* src, int sw, int sh, int channels, fl
 bool cascade_supported(const BlurTaps* taps);
 cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, float* dec, int dec_w, int dec_h,
                                 int dec_pitch, bool keep_all, int sm_count, int mode, int part, cudaStream_t s);
+// the latency-bound small octaves (at most one 32 x 32 tile per SM) in one launch; sync = 1 + kMaxOctaves zeroed ints
+bool tail_eligible(const OctaveDesc& od, int sm_count);
+cudaError_t launch_tail(const OctaveDesc* octs, int first, int octaves, const BlurTaps* taps, bool keep_all, int* sync,
+                        int sm_count, cudaStream_t s);
 
 // detect.cu
 struct SortScratch {
@@ -45,6 +49,9 @@ cudaError_t launch_canary_tail(const void* p, size_t words, unsigned pattern, un
                                cudaStream_t s);
 cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int border, int threshold, Cand* cands,
                            int cap, Counters* counters, int form, cudaStream_t s);
+bool extrema_multi_supported(int border, int form);
+cudaError_t launch_extrema_multi(const OctaveDesc* octs, int first, int n, int dogs, int threshold, Cand* cands, int cap,
+                                 Counters* counters, cudaStream_t s);
 cudaError_t launch_refine(const PyramidDesc* d_pyr, const Cand* cands, KpCore* raw,
                           Counters* counters, const StageParams& sp, int sm_count, cudaStream_t s);
 cudaError_t launch_orient(const PyramidDesc* d_pyr, const KpCore* raw, KpCore* oriented,

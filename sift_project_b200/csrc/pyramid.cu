@@ -10,6 +10,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -180,13 +181,15 @@ struct CascadeGeom {
     static constexpr size_t kSmem = (size_t)(A_FLOATS + T_FLOATS + B_FLOATS) * sizeof(float);
 };
 
-struct CascadeArgs {
+struct CascadePlanes {
     const float* in;      // level 0 of this launch (G0 or G3)
     float* g[3];          // level outputs (nullable: not stored)
     float* d[3];          // d[l] = level(l+1) - level(l)
     float* dec;           // decimated copy of the LAST level (nullable)
     int w, h, pitch;
     int dec_w, dec_h, dec_pitch;
+};
+struct CascadeArgs : CascadePlanes {
     BlurTaps taps[3];
 };
 
@@ -282,17 +285,20 @@ __device__ unsigned long long g_phase[16];
 
 // TWP x THP = tile, NTP = threads, MINB = CTAs per SM.  64 x 64 / 384 / 2 for large octaves; 32 x 32 / 128 / 4
 // for octaves that would not fill the GPU with 64 x 64 tiles (a lone CTA takes 10-18 us per tile).
-template <int R1, int R2, int R3, int TWP, int THP, int NTP, int MINB>
-__global__ void __launch_bounds__(NTP, MINB) k_cascade(const CascadeArgs a) {
+// One tile.  `a`: the planes of this launch; `taps`: its three tap sets (kernel-parameter space: the FMAs take them
+// as constant-bank operands); (bx, by): the tile.  COHERENT: the input may have been written by another CTA of the
+// SAME launch (k_tail), so it must not come through the non-coherent (LDG.NC) path.
+template <int R1, int R2, int R3, int TWP, int THP, int NTP, bool COHERENT>
+__device__ __forceinline__ void cascade_tile(const CascadePlanes& a, const BlurTaps* __restrict__ taps, int bx, int by,
+                                             float* __restrict__ smem) {
     using G = CascadeGeom<R1, R2, R3, TWP, THP>;
     SB_PHASE_INIT
-    extern __shared__ __align__(16) float smem[];
     float* sA = smem;
     float* sT = sA + G::A_FLOATS;
     float* sB = sT + G::T_FLOATS;
     const int tid = threadIdx.x;
     const int w = a.w, h = a.h, pitch = a.pitch;
-    const int tx0 = blockIdx.x * TWP, ty0 = blockIdx.y * THP;
+    const int tx0 = bx * TWP, ty0 = by * THP;
     const int gx0 = tx0 - G::HX0, gy0 = ty0 - G::HY0;
     const bool interior = gx0 >= 0 && gy0 >= 0 && (tx0 + TWP + G::HX0) <= w && (ty0 + THP + G::HY0) <= h;
 
@@ -308,7 +314,8 @@ __global__ void __launch_bounds__(NTP, MINB) k_cascade(const CascadeArgs a) {
         for (int idx = tid; idx < G::H0 * G::W0; idx += NTP) {
             const int r = idx / G::W0, c = idx - r * G::W0;
             const int gy = min(max(gy0 + r, 0), h - 1), gx = min(max(gx0 + c, 0), w - 1);
-            sA[idx] = __ldg(a.in + (size_t)gy * pitch + gx);
+            const float* src = a.in + (size_t)gy * pitch + gx;
+            sA[idx] = COHERENT ? __ldcg(src) : __ldg(src);
         }
     }
     __syncthreads();
@@ -341,10 +348,10 @@ __global__ void __launch_bounds__(NTP, MINB) k_cascade(const CascadeArgs a) {
     };
 
     // ---- level 1: sA -> sT -> sB ----
-    cascade_hpass<NTP, R1, G::W0, G::W1, G::HX0 - G::HX1>(sA, sT, G::H0, a.taps[0]);
+    cascade_hpass<NTP, R1, G::W0, G::W1, G::HX0 - G::HX1>(sA, sT, G::H0, taps[0]);
     __syncthreads();
     SB_PHASE(1);
-    cascade_vpass<NTP, R1, G::W1>(sT + (G::HY0 - G::HY1 - R1) * G::W1, G::H1, a.taps[0],
+    cascade_vpass<NTP, R1, G::W1>(sT + (G::HY0 - G::HY1 - R1) * G::W1, G::H1, taps[0],
                              [&](int y, int q, const float4 (&acc)[4]) {
 #pragma unroll
                                  for (int k = 0; k < 4; ++k)
@@ -371,10 +378,10 @@ __global__ void __launch_bounds__(NTP, MINB) k_cascade(const CascadeArgs a) {
 
     if (G::NL == 3) {
         // ---- level 2: sB -> sT -> sA (the input is dead by now) ----
-        cascade_hpass<NTP, R2, G::W1, G::W2, G::HX1 - G::HX2>(sB, sT, G::H1, a.taps[1]);
+        cascade_hpass<NTP, R2, G::W1, G::W2, G::HX1 - G::HX2>(sB, sT, G::H1, taps[1]);
         __syncthreads();
     SB_PHASE(5);
-        cascade_vpass<NTP, R2, G::W2>(sT + (G::HY1 - G::HY2 - R2) * G::W2, G::H2, a.taps[1],
+        cascade_vpass<NTP, R2, G::W2>(sT + (G::HY1 - G::HY2 - R2) * G::W2, G::H2, taps[1],
                                  [&](int y, int q, const float4 (&acc)[4]) {
 #pragma unroll
                                      for (int k = 0; k < 4; ++k)
@@ -397,25 +404,112 @@ __global__ void __launch_bounds__(NTP, MINB) k_cascade(const CascadeArgs a) {
         }
     SB_PHASE(8);
         // ---- level 3: sA -> sT -> registers -> HBM ----
-        cascade_hpass<NTP, (R3 > 0 ? R3 : 1), G::W2, TWP, G::HX2>(sA, sT, G::H2, a.taps[2]);
+        cascade_hpass<NTP, (R3 > 0 ? R3 : 1), G::W2, TWP, G::HX2>(sA, sT, G::H2, taps[2]);
         __syncthreads();
     SB_PHASE(9);
-        cascade_vpass<NTP, (R3 > 0 ? R3 : 1), TWP>(sT + (G::HY2 - R3) * TWP, THP, a.taps[2],
+        cascade_vpass<NTP, (R3 > 0 ? R3 : 1), TWP>(sT + (G::HY2 - R3) * TWP, THP, taps[2],
                                            [&](int y, int q, const float4 (&acc)[4]) {
                                                store_level(a.g[2], a.d[2], sA, G::W2, G::HX2, G::HY2, y, q, acc, true);
                                            });
     } else {
         // ---- two-level variant: level 2 is the last: sB -> sT -> registers -> HBM ----
-        cascade_hpass<NTP, R2, G::W1, TWP, G::HX1>(sB, sT, G::H1, a.taps[1]);
+        cascade_hpass<NTP, R2, G::W1, TWP, G::HX1>(sB, sT, G::H1, taps[1]);
         __syncthreads();
     SB_PHASE(10);
-        cascade_vpass<NTP, R2, TWP>(sT + (G::HY1 - R2) * TWP, THP, a.taps[1],
+        cascade_vpass<NTP, R2, TWP>(sT + (G::HY1 - R2) * TWP, THP, taps[1],
                               [&](int y, int q, const float4 (&acc)[4]) {
                                   store_level(a.g[1], a.d[1], sB, G::W1, G::HX1, G::HY1, y, q, acc, true);
                               });
     }
     SB_PHASE(15);
 }
+
+template <int R1, int R2, int R3, int TWP, int THP, int NTP, int MINB>
+__global__ void __launch_bounds__(NTP, MINB) k_cascade(const CascadeArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    cascade_tile<R1, R2, R3, TWP, THP, NTP, false>(a, a.taps, blockIdx.x, blockIdx.y, smem);
+}
+
+// ------------------------------------------------------------------------------------------
+// The tail of the pyramid in ONE launch.  Octaves of at most one 32 x 32 tile per SM are latency-bound: a launch
+// lasts one tile's serial phases (~5 us) plus the launch gap, two launches per octave, seven such octaves below a
+// 4K image, and each octave needs the previous one's decimated G3 (sift.cpp:187-199).  k_tail runs the same tile
+// code (cascade_tile<.., 32, 32, 512>, hence the same bits) for all of them from a ticket counter: CTAs draw work
+// items in an order in which every item depends only on items with LOWER tickets -- group g = the first-kernel
+// tiles of tail octave g, then the second-kernel tiles of octave g - 1 -- so a waiting CTA only ever waits for
+// CTAs that are already running: no co-residency requirement (not a cooperative launch), no deadlock whatever
+// else shares the GPU.  Hand-over between octaves: per-octave "tiles done" counters, release = CTA barrier +
+// __threadfence + atomicAdd by one thread, acquire = ld.acquire polled by one thread + CTA barrier; consumers read
+// the fresh planes through L2 (cp.async.cg / ld.cg).
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxTail = 12;
+constexpr int TAIL_NT = 512;
+struct TailOct {
+    CascadePlanes a, b;   // G0 -> G1..G3, D0..D2, next base | G3 -> (G4, G5) D3, D4
+    int tiles_x, tiles;
+};
+struct TailArgs {
+    int n, total;
+    int begin[kMaxTail + 2];   // first ticket of group g
+    TailOct oct[kMaxTail];
+    BlurTaps taps_a[3], taps_b[3];
+    int* sync;                 // [0] ticket counter, [1 + o] first-kernel tiles of tail octave o done; zeroed per call
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(TAIL_NT, 2) k_tail(const TailArgs t) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ int s_ticket;
+    for (;;) {
+        __syncthreads();   // the previous item's shared-memory reads and its s_ticket reads are over
+        if (threadIdx.x == 0) s_ticket = atomicAdd(t.sync, 1);
+        __syncthreads();
+        const int k = s_ticket;
+        if (k >= t.total) return;
+        int g = 0;
+        while (k >= t.begin[g + 1]) ++g;
+        int i = k - t.begin[g];
+        const int na = g < t.n ? t.oct[g].tiles : 0;
+        const bool first = i < na;
+        const int o = first ? g : g - 1;
+        if (!first) i -= na;
+        const int dep = first ? o - 1 : o;   // the octave whose first-kernel tiles this item reads
+        if (dep >= 0) {
+            if (threadIdx.x == 0) {
+                const int need = t.oct[dep].tiles;
+                int spins = 0;
+                while (ld_acquire_gpu(t.sync + 1 + dep) < need) {
+                    __nanosleep(32);
+                    if (++spins > (1 << 21)) __trap();   // seconds: a lost hand-over must fail, not hang
+                }
+            }
+            __syncthreads();
+        }
+        const int tiles_x = t.oct[o].tiles_x;
+        const int by = i / tiles_x, bx = i - by * tiles_x;
+        if (first) {
+            const CascadePlanes p = t.oct[o].a;
+            cascade_tile<4, 5, 6, 32, 32, TAIL_NT, true>(p, t.taps_a, bx, by, smem);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(t.sync + 1 + o, 1);
+            }
+        } else {
+            const CascadePlanes p = t.oct[o].b;
+            cascade_tile<8, 10, 0, 32, 32, TAIL_NT, true>(p, t.taps_b, bx, by, smem);
+        }
+    }
+}
+
+constexpr size_t kTailSmem = CascadeGeom<4, 5, 6, 32, 32>::kSmem > CascadeGeom<8, 10, 0, 32, 32>::kSmem
+                                 ? CascadeGeom<4, 5, 6, 32, 32>::kSmem
+                                 : CascadeGeom<8, 10, 0, 32, 32>::kSmem;
 
 template <int R1, int R2, int R3>
 cudaError_t launch_cascade_t(const CascadeArgs& a, int sm_count, cudaStream_t s) {
@@ -626,6 +720,8 @@ cudaError_t pyramid_init() {
     SB_CASC_ATTR(4, 5, 6, 32, 32, 128, 4) SB_CASC_ATTR(8, 10, 0, 32, 32, 128, 4)
     SB_CASC_ATTR(4, 5, 6, 32, 32, 512, 1) SB_CASC_ATTR(8, 10, 0, 32, 32, 512, 1)
 #undef SB_CASC_ATTR
+    if ((e = cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmem)) != cudaSuccess)
+        return e;
     if (g_stream_encode == nullptr) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -726,6 +822,55 @@ cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, floa
     b.taps[0] = taps[4]; b.taps[1] = taps[5]; b.taps[2] = taps[5];
     if (!stream) return launch_cascade_t<8, 10, 0>(b, sm_count, s);
     return launch_stream_t<StreamB>(b, sm_count, s);
+}
+
+// Octaves that launch_cascade_t would run as at most one 32 x 32 tile per SM (its third form): the tail.
+bool tail_eligible(const OctaveDesc& od, int sm_count) {
+    return ((od.w + 31) / 32) * ((od.h + 31) / 32) <= sm_count;
+}
+
+// Octaves first .. octaves - 1 (all tail_eligible) in one launch; `sync` = 1 + n zeroed ints.  Same planes, bit for
+// bit, as launch_octave_fused(part 1), (part 2) per octave.
+cudaError_t launch_tail(const OctaveDesc* octs, int first, int octaves, const BlurTaps* taps, bool keep_all, int* sync,
+                        int sm_count, cudaStream_t s) {
+    const int n = octaves - first;
+    if (n < 1 || n > kMaxTail) return cudaErrorInvalidValue;
+    TailArgs t;
+    memset(&t, 0, sizeof t);
+    t.n = n;
+    t.sync = sync;
+    for (int i = 0; i < 3; ++i) t.taps_a[i] = taps[1 + i];
+    t.taps_b[0] = taps[4]; t.taps_b[1] = taps[5]; t.taps_b[2] = taps[5];
+    for (int i = 0; i < n; ++i) {
+        const OctaveDesc& od = octs[first + i];
+        TailOct& to = t.oct[i];
+        to.tiles_x = (od.w + 31) / 32;
+        to.tiles = to.tiles_x * ((od.h + 31) / 32);
+        CascadePlanes& a = to.a;
+        a.in = od.G[0];
+        a.g[0] = od.G[1]; a.g[1] = od.G[2]; a.g[2] = od.G[3];
+        a.d[0] = od.D[0]; a.d[1] = od.D[1]; a.d[2] = od.D[2];
+        a.w = od.w; a.h = od.h; a.pitch = od.pitch;
+        if (first + i + 1 < octaves) {   // next base = G3 decimated, sift.cpp:195-196
+            const OctaveDesc& nx = octs[first + i + 1];
+            a.dec = nx.G[0]; a.dec_w = nx.w; a.dec_h = nx.h; a.dec_pitch = nx.pitch;
+        }
+        CascadePlanes& b = to.b;
+        b.in = od.G[3];
+        b.g[0] = keep_all ? od.G[4] : nullptr; b.g[1] = keep_all ? od.G[5] : nullptr;
+        b.d[0] = od.D[3]; b.d[1] = od.D[4];
+        b.w = od.w; b.h = od.h; b.pitch = od.pitch;
+    }
+    int total = 0;
+    for (int g = 0; g <= n; ++g) {   // group g: first kernel of octave g, second kernel of octave g - 1
+        t.begin[g] = total;
+        if (g < n) total += t.oct[g].tiles;
+        if (g >= 1) total += t.oct[g - 1].tiles;
+    }
+    t.begin[n + 1] = total;
+    t.total = total;
+    k_tail<<<std::min(sm_count, total), TAIL_NT, kTailSmem, s>>>(t);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_prepare_u8(const uint8_t* src, int sw, int sh, int ch, float* dst, int dw, int dh,

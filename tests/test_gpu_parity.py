@@ -198,6 +198,35 @@ def test_scale_space_kernels_write_exactly_their_planes(ctx, mode):
     ctx.debug_options()
 
 
+def test_tail_kernel_equals_octave_by_octave_launches(ctx):
+    """k_tail (all small octaves from one ticket counter, hand-over between octaves inside the launch) and the
+    multi-octave extrema launch against one launch per octave: every plane and the records bit-identical, repeated
+    (the hand-over is a race if it is wrong), with and without the debug planes, graph and plain launches."""
+    for h, w, seed in ((300, 400, 5), (97, 131, 1), (768, 1024, 9), (33, 41, 2), (150, 700, 3)):
+        img = O.synth_image(max(h, 8), max(w, 8), seed=seed)[:h, :w]
+        for keep in (True, False):
+            ctx.debug_options(keep_all_planes=keep)
+            ctx.tail_kernel(False)
+            ref = ctx.detect(img)
+            octs = ctx.stats()["octaves"]
+            layers = range(6) if keep else range(4)
+            planes = [[ctx.gaussian(o, l) for l in layers] + [ctx.dog(o, l) for l in range(5)] for o in range(octs)]
+            n_ref = ctx.stats()["extrema"]
+            ctx.tail_kernel(True)
+            for rep in range(6):
+                ctx.launch_plan(use_graph=rep & 1)
+                got = ctx.detect(img)
+                assert got.tobytes() == ref.tobytes(), (h, w, keep, rep)
+                assert ctx.stats()["extrema"] == n_ref
+                if rep < 2:
+                    for o in range(octs):
+                        mine = [ctx.gaussian(o, l) for l in layers] + [ctx.dog(o, l) for l in range(5)]
+                        for k, (x, y) in enumerate(zip(mine, planes[o])):
+                            assert np.array_equal(x, y), (h, w, keep, o, k)
+    ctx.launch_plan(use_graph=1)
+    ctx.debug_options()
+
+
 def test_graph_replay_equals_plain_launches(ctx, synth):
     """The CUDA-graph launch plan (forked octave chain) and plain single-stream launches run the same kernels on
     the same data: identical bytes; one graph per image size / parameter set, re-captured only on a change."""
@@ -498,14 +527,21 @@ def test_profile_marks_add_up_to_the_stage_profile(ctx):
     time, the fused pyramid bracketed kernel by kernel on octave 0 and per octave below."""
     img = O.synth_image(300, 400, seed=5)
     ctx.set_profiling(True)
+    ctx.tail_kernel(False)
     ctx.detect(img)
     ms, nl = ctx.profile()
     marks = ctx.profile_marks()
-    ctx.set_profiling(False)
     octs = ctx.stats()["octaves"]
     assert [st for st, _ in marks][:4] == ["input", "pyramid", "pyramid", "extrema"]
     assert sum(1 for st, _ in marks if st == "pyramid") == octs + 1
     assert nl["pyramid"] == 2 * octs
+    ctx.tail_kernel(True)      # octaves 1.. of the 600 x 800 base are at most one tile per SM: one launch for all
+    ctx.detect(img)
+    ms, nl = ctx.profile()
+    marks = ctx.profile_marks()
+    ctx.set_profiling(False)
+    assert nl["pyramid"] == 3 and nl["extrema"] == 2
+    assert [st for st, _ in marks][:6] == ["input", "pyramid", "pyramid", "extrema", "pyramid", "extrema"]
     for st in S.SiftContext.STAGES:
         assert abs(sum(t for s_, t in marks if s_ == st) - ms[st]) < 1e-3, st
     assert all(t >= 0 for _, t in marks)
