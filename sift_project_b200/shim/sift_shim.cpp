@@ -25,6 +25,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "sift.hh"
@@ -86,6 +87,23 @@ struct PinnedBuf {
     }
 };
 
+// f(begin, end) -> bool over [0, n) in up to 8 chunks on as many threads (one per 2 M elements); AND of the results
+template <typename F>
+bool parallel_chunks(size_t n, F f) {
+    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t parts = std::max<size_t>(1, std::min<size_t>({(size_t)8, hw, n >> 21}));
+    if (parts == 1) return f((size_t)0, n);
+    std::vector<char> ok(parts, 1);
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < parts; ++t)
+        pool.emplace_back([&, t] { ok[t] = f(n * t / parts, n * (t + 1) / parts) ? 1 : 0; });
+    ok[0] = f((size_t)0, n / parts) ? 1 : 0;
+    for (std::thread& th : pool) th.join();
+    bool all = true;
+    for (char c : ok) all = all && c;
+    return all;
+}
+
 [[noreturn]] void fail(sift_b200_ctx* c, const char* what) {
     throw std::runtime_error(std::string(what) + ": " + sift_b200_last_error(c));
 }
@@ -117,21 +135,31 @@ std::vector<Keypoint> detect_keypoints_and_descriptors(const Image& img, const b
 
     // Image::data holds doubles 0..255 that came from 8-bit files (image_io.cpp:27-33): ship them
     // as bytes when that is lossless, as floats otherwise.
+    // One pass over the doubles (66 MB for a 4K gray image: the conversion, not the GPU, is what a caller waits for,
+    // so it is split over a few host threads), a second one only when some pixel is not a whole number in 0..255.
     const size_t n = img.data.size();
-    bool bytes_ok = true;
-    for (size_t i = 0; i < n && bytes_ok; ++i) {
-        const double v = img.data[i];
-        bytes_ok = v >= 0.0 && v <= 255.0 && v == std::floor(v);
-    }
     std::vector<Keypoint> out(std::max<size_t>(4096, (size_t)img.width * img.height / 16));
     int count = 0, rc;
     thread_local PinnedBuf staging;
-    if (bytes_ok) {
-        uint8_t* px = static_cast<uint8_t*>(staging.get(n));
-        for (size_t i = 0; i < n; ++i) px[i] = (uint8_t)img.data[i];
-    } else {
-        float* px = static_cast<float*>(staging.get(n * sizeof(float)));
-        for (size_t i = 0; i < n; ++i) px[i] = (float)img.data[i];
+    uint8_t* bytes = static_cast<uint8_t*>(staging.get(n * sizeof(float)));   // room for the float form as well
+    const double* src = img.data.data();
+    const bool bytes_ok = parallel_chunks(n, [&](size_t b, size_t e) {
+        bool ok = true;
+        for (size_t i = b; i < e; ++i) {
+            const double v = src[i];
+            const double c = (v >= 0.0 && v <= 255.0) ? v : 0.0;
+            const uint8_t q = (uint8_t)c;
+            bytes[i] = q;
+            ok &= (double)q == v;
+        }
+        return ok;
+    });
+    if (!bytes_ok) {
+        float* px = static_cast<float*>(staging.p);
+        parallel_chunks(n, [&](size_t b, size_t e) {
+            for (size_t i = b; i < e; ++i) px[i] = (float)src[i];
+            return true;
+        });
     }
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (bytes_ok)
