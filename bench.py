@@ -528,7 +528,10 @@ def run_b200(args):
         # base (1); second kernel reads G3 (4), writes D3, D4 (8)
         per_kernel = None
         pyr_marks = [i for i, (st, _) in enumerate(marks) if st == "pyramid"]
-        if len(pyr_marks) >= 2 and nl["pyramid"] == 2 * (len(pyr_marks) - 1):   # fused path: octave 0 kernel by kernel
+        fused = (len(pyr_marks) >= 2 and pyr_marks[1] == pyr_marks[0] + 1 and pyr_marks[1] + 1 < len(marks)
+                 and marks[pyr_marks[1] + 1][0] == "extrema")
+        tail = None
+        if fused:   # fused path: octave 0 kernel by kernel
             bw, bh = (2 * W, 2 * H)
             px0 = bw * bh
             per_kernel = []
@@ -543,10 +546,16 @@ def run_b200(args):
                 per_kernel.append({"kernel": "octave 0: 3x3x3 extrema scan (k_extrema4), reads D0..D4", "ms": t,
                                    "algorithmic_bytes": 20.0 * px0, "achieved": 20.0 * px0 / (t * 1e-3) / 1e9,
                                    "frac": 20.0 * px0 / (t * 1e-3) / 1e9 / hbm_peak})
-        roof = {"bound": "hbm", "kernel": "pyramid: fused cascade G0->G1..G3,D0..D2,next base + G3->D3,D4 (k_stream on octaves >= 2 Mpx, k_cascade below), all octaves of one image", "achieved": achieved,
+            octs = c0.stats()["octaves"]
+            if nl["pyramid"] % 2 == 1 and pyr_marks[-1] + 1 < len(marks):   # ... + one launch for the small octaves
+                n_tail = octs - (nl["pyramid"] - 1) // 2
+                tail = {"kernel": "k_tail: both cascade kernels of the last %d octaves in one ticket-ordered launch" % n_tail,
+                        "ms": marks_acc[pyr_marks[-1]] / reps, "octaves": n_tail,
+                        "extrema_ms": marks_acc[pyr_marks[-1] + 1] / reps if marks[pyr_marks[-1] + 1][0] == "extrema" else None}
+        roof = {"bound": "hbm", "kernel": "pyramid: fused cascade G0->G1..G3,D0..D2,next base + G3->D3,D4 (k_stream on octaves >= 2 Mpx, k_cascade below, k_tail for the octaves of <= 1 tile per SM), all octaves of one image", "achieved": achieved,
                 "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                 "algorithmic_bytes": pyr_bytes, "ms": stages["pyramid"], "launches": nl["pyramid"],
-                "peak_source": peak_src, "per_kernel": per_kernel,
+                "peak_source": peak_src, "per_kernel": per_kernel, "tail": tail,
                 "whole_detect": {"algorithmic_bytes": HBM_BYTES_PER_INPUT_PIXEL * W * H, "ms": total_ms,
                                  "frac": HBM_BYTES_PER_INPUT_PIXEL * W * H / (total_ms * 1e-3) / 1e9 / hbm_peak}}
 
