@@ -826,7 +826,8 @@ cudaError_t launch_octave_fused(const OctaveDesc& od, const BlurTaps* taps, floa
 
 // Octaves that launch_cascade_t would run as at most one 32 x 32 tile per SM (its third form): the tail.
 bool tail_eligible(const OctaveDesc& od, int sm_count) {
-    return ((od.w + 31) / 32) * ((od.h + 31) / 32) <= sm_count;
+    static const int mult = getenv("SIFT_B200_TAIL_TILES") ? atoi(getenv("SIFT_B200_TAIL_TILES")) : 1;   // experiments
+    return ((od.w + 31) / 32) * ((od.h + 31) / 32) <= mult * sm_count;
 }
 
 // Octaves first .. octaves - 1 (all tail_eligible) in one launch; `sync` = 1 + n zeroed ints.  Same planes, bit for
@@ -869,7 +870,8 @@ cudaError_t launch_tail(const OctaveDesc* octs, int first, int octaves, const Bl
     }
     t.begin[n + 1] = total;
     t.total = total;
-    k_tail<<<std::min(sm_count, total), TAIL_NT, kTailSmem, s>>>(t);
+    static const int ctas = getenv("SIFT_B200_TAIL_CTAS") ? atoi(getenv("SIFT_B200_TAIL_CTAS")) : 1;   // experiments
+    k_tail<<<std::min(ctas * sm_count, total), TAIL_NT, kTailSmem, s>>>(t);
     return cudaGetLastError();
 }
 
