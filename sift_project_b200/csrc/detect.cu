@@ -19,10 +19,28 @@ __device__ __forceinline__ float ldg(const float* p) { return __ldg(p); }
 // atan2 for the gradient angle: odd minimax polynomial of degree 17 on [0, 1] (Abramowitz & Stegun
 // 4.4.49, |error| <= 2e-8) + quadrant fix-up, with an approximate reciprocal for the ratio; total
 // error ~1e-7 rad, the same order as atan2f's, at about half the instructions and no slow path.
+// MUFU without the denormal pre- / post-scaling that the non-ftz forms wrap around it (4-5 instructions each in the
+// sample loops): identical bits for normal arguments; the callers treat sub-normal arguments as zero.
+constexpr float kFltMin = 1.17549435e-38f;
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float exp_ftz(float x) {   // __expf for results that are normal numbers
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950216293334961f));
+    return r;
+}
 __device__ __forceinline__ float fast_atan2(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float a = mx > 0.f ? __fdividef(mn, mx) : 0.f;
+    const float a = mx >= kFltMin ? mn * rcp_ftz(mx) : 0.f;
     const float s = a * a;
     float p = 0.0028662257f;
     p = fmaf(p, s, -0.0161657367f);
@@ -507,9 +525,9 @@ k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, Kp
             const float dx = ldg(c + 1) - ldg(c - 1);
             const float dy = ldg(c - pitch) - ldg(c + pitch);  // up minus down, sift.cpp:483
             const float g2 = dx * dx + dy * dy;
-            const float mag = g2 > 0.f ? g2 * rsqrtf(g2) : 0.f;
+            const float mag = g2 >= kFltMin ? g2 * rsqrt_ftz(g2) : 0.f;
             const float ang = fast_atan2(dy, dx);
-            const float wgt = __expf((float)(i_off * i_off + j_off * j_off) * neg_inv_denom);
+            const float wgt = exp_ftz((float)(i_off * i_off + j_off * j_off) * neg_inv_denom);
             int b = (int)roundf((ang + 3.14159265358979323846f) * bins_per_rad);
             b = (b < nb) ? b : 0;  // sift.cpp:489-490: bin 0 <-> angle -pi
             b = max(b, 0);
@@ -753,6 +771,17 @@ constexpr int DESC_WORDS = DESC_GRID * DESC_GRID * 8;   // per histogram copy
 #endif
 constexpr int DESC_STRIDE = DESC_WORDS + SB_DESC_PAD;
 
+// position of the (n + 1)-th set bit of m, 32 if there are fewer
+__device__ __forceinline__ int nth_set_bit(unsigned m, int n) {
+    int pos = 0;
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const int c = __popc(m & ((1u << w) - 1u));
+        if (n >= c) { n -= c; pos += w; m >>= w; }
+    }
+    return (m & 1u) && n == 0 ? pos : 32;
+}
+
 __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_CTAS)
 k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ oriented,
            const int* __restrict__ final_order, Counters* __restrict__ counters,
@@ -762,6 +791,7 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned* hist = &s_hist[warp][0][0];
     unsigned* my_hist = s_hist[warp][lane & (DESC_COPIES - 1)];
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int n = min(counters->n_final, cap_final);
     const double mag_bound = sp.range ? fmax(1.4142135623730951 * ((double)sp.range[1] - (double)sp.range[0]), 1e-30) * 1.001
                                       : sp.mag_bound;
@@ -821,29 +851,40 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
             }
             const int total = __shfl_sync(FULL, off, 31);
             off -= cnt;  // exclusive
+            // The non-empty rows, compacted: lane c then holds the c-th of them (first sample `c_off`, strictly
+            // increasing; first column and row slot packed in `c_row`).  Inside the sample loop a lane finds its row
+            // without a search: the rows that start in (s0, s0 + 32] set one bit each (REDUX.OR), a lane's row is the
+            // row of sample s0 plus the bits below its own position.
+            // (compaction by shuffles: shared memory for it would push five CTAs over the 196 KB carve-out step)
+            const unsigned nonempty = __ballot_sync(FULL, cnt > 0);
+            const int src = nth_set_bit(nonempty, lane);
+            const int src_off = __shfl_sync(FULL, off, src & 31);
+            const int c_row = __shfl_sync(FULL, lo * 32 + lane, src & 31);
+            const int c_off = src < 32 ? src_off : 0x7fffffff;
+            int kb = 0;   // compact row of sample s0
             for (int s0 = 0; s0 < total; s0 += 32) {
                 const int s = s0 + lane;
-                // row slot k = the last lane whose exclusive offset is <= s
-                int k = 0;
-#pragma unroll
-                for (int step = 16; step >= 1; step >>= 1) {
-                    const int o = __shfl_sync(FULL, off, k + step);
-                    if (o <= s) k += step;
-                }
-                const int off_k = __shfl_sync(FULL, off, k);
-                const int lo_k = __shfl_sync(FULL, lo, k);
+                const unsigned p = (unsigned)(c_off - s0 - 1);
+                const unsigned starts = __reduce_or_sync(FULL, p < 32u ? 1u << p : 0u);
+                const int k = kb + __popc(starts & lt_mask);
+                kb += __popc(starts);
+                const int off_k = __shfl_sync(FULL, c_off, k);
+                const int row_k = __shfl_sync(FULL, c_row, k);
                 if (s >= total) continue;
-                const int col = lo_k + (s - off_k);
-                const int rw = row0 + k;
-                const float rr = ((float)col * sa + (float)rw * ca) * inv_hw;
-                const float cr = ((float)col * ca - (float)rw * sa) * inv_hw;
+                const int col = (row_k >> 5) + (s - off_k);
+                const int rw = row0 + (row_k & 31);
+                // (contractions written out: which product is rounded first must not depend on the compiler's mood --
+                // it flipped once and moved one descriptor byte in 3327 keypoints)
+                const float fcol = (float)col, frow = (float)rw;
+                const float rr = fmaf(ca, frow, __fmul_rn(sa, fcol)) * inv_hw;
+                const float cr = fmaf(ca, fcol, -__fmul_rn(sa, frow)) * inv_hw;
                 const float rb = rr + 1.5f, cb = cr + 1.5f;  // + DESC_HIST_WIDTH/2 - 0.5 (integer 4/2)
                 if (!(rb > -1.0f && rb < 4.0f && cb > -1.0f && cb < 4.0f)) continue;
                 const float* c = img + (size_t)(rw + y) * pitch + (col + x);
                 const float dx = ldg(c + 1) - ldg(c - 1);
                 const float dy = ldg(c - pitch) - ldg(c + pitch);
-                const float g2 = dx * dx + dy * dy;
-                const float mag = g2 > 0.f ? g2 * rsqrtf(g2) : 0.f;
+                const float g2 = fmaf(dx, dx, __fmul_rn(dy, dy));
+                const float mag = g2 >= kFltMin ? g2 * rsqrt_ftz(g2) : 0.f;
 #ifndef SB_DESC_DIET
 #define SB_DESC_DIET 0
 #endif
@@ -863,7 +904,7 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
                 if (ang < 0.f) ang += 6.283185307179586f;
                 if (ang >= 6.283185307179586f) ang -= 6.283185307179586f;
                 const float ob = ang * (8.0f / 6.283185307179586f);
-                const float wgt = __expf(-(rr * rr + cr * cr) * 0.125f);
+                const float wgt = exp_ftz(-(rr * rr + cr * cr) * 0.125f);
                 const float m = mag * wgt * fix;
                 constexpr float kMagic = 12582912.0f;          // 1.5 * 2^23, bit pattern 0x4B400000
                 const float tr = (rb - 0.5f) + kMagic, tc = (cb - 0.5f) + kMagic, to = (ob - 0.5f) + kMagic;
@@ -898,8 +939,8 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
                 if (ang < 0.f) ang = 0.f;
                 if (ang >= 6.283185307179586f) ang -= 6.283185307179586f;
                 const float ob = ang * (8.0f / 6.283185307179586f);
-                const float wgt = __expf(-(rr * rr + cr * cr) * 0.125f);
-                const float m = mag * wgt * fix;
+                const float wgt = exp_ftz(-fmaf(rr, rr, __fmul_rn(cr, cr)) * 0.125f);
+                const float m = __fmul_rn(__fmul_rn(mag, wgt), fix);
                 const float fbr = floorf(rb), fbc = floorf(cb), fbo = floorf(ob);
                 const int br = (int)fbr, bc = (int)fbc, bo = (int)fbo;
                 const float fr = rb - fbr, fc = cb - fbc, fo = ob - fbo;
@@ -959,13 +1000,13 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
         uint8_t* rec = records + (size_t)i * 168;
         *reinterpret_cast<uint32_t*>(rec + 40 + 4 * lane) = packed;
         *reinterpret_cast<uint32_t*>(desc + (size_t)i * 128 + 4 * lane) = packed;
-        if (lane == 0) {
-            *reinterpret_cast<double*>(rec + 0) = kp.x;
-            *reinterpret_cast<double*>(rec + 8) = kp.y;
-            *reinterpret_cast<int*>(rec + 16) = kp.octave;
-            *reinterpret_cast<int*>(rec + 20) = kp.layer;
-            *reinterpret_cast<double*>(rec + 24) = kp.size;
-            *reinterpret_cast<double*>(rec + 32) = kp.pori;
+        if (lane < 5) {
+            // the 40-byte head of the record is copied from the keypoint list again (L2 hit) instead of being kept in
+            // 10 registers through the sample loop; the pointer is laundered so that the loads are not merged with
+            // the ones at the top
+            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(oriented + final_order[i]);
+            asm volatile("" : "+l"(src));
+            *reinterpret_cast<unsigned long long*>(rec + 8 * lane) = src[lane];
         }
         __syncwarp();
     }
