@@ -880,9 +880,10 @@ k_describe(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ orien
                 const float cr = fmaf(ca, fcol, -__fmul_rn(sa, frow)) * inv_hw;
                 const float rb = rr + 1.5f, cb = cr + 1.5f;  // + DESC_HIST_WIDTH/2 - 0.5 (integer 4/2)
                 if (!(rb > -1.0f && rb < 4.0f && cb > -1.0f && cb < 4.0f)) continue;
-                const float* c = img + (size_t)(rw + y) * pitch + (col + x);
-                const float dx = ldg(c + 1) - ldg(c - 1);
-                const float dy = ldg(c - pitch) - ldg(c + pitch);
+                const int ic = (rw + y) * pitch + (col + x);   // 32-bit indices: a plane has < 2^31 elements
+                const int iu = ic - pitch, id = ic + pitch;
+                const float dx = ldg(img + ic + 1) - ldg(img + ic - 1);
+                const float dy = ldg(img + iu) - ldg(img + id);
                 const float g2 = fmaf(dx, dx, __fmul_rn(dy, dy));
                 const float mag = g2 >= kFltMin ? g2 * rsqrt_ftz(g2) : 0.f;
 #ifndef SB_DESC_DIET
