@@ -8,6 +8,7 @@
 // bit-reproducible although list compaction uses atomics (the final order is re-established by an
 // exact sort on the reference's own comparison key).
 #include <cstdlib>
+#include <type_traits>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -517,22 +518,30 @@ k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, Kp
         const int j_lo = max(-radius, 1 - y), j_hi = min(radius, H - 2 - y);
         const int side = i_hi - i_lo + 1;
         const int total = (side > 0 && j_hi >= j_lo) ? side * (j_hi - j_lo + 1) : 0;
+        // s / side by multiplication: floor(s / side) == umulhi(s, ceil(2^32 / side)) while s * side < 2^32 (windows of
+        // up to 1024 columns; anything wider -- only reachable with an absurd ori_sigma_factor -- divides)
+        const unsigned magic = side > 0 ? (unsigned)((0x100000000ull + (unsigned)side - 1u) / (unsigned)side) : 0u;
+        auto sample_loop = [&](auto small_tag) {
+        constexpr bool SMALL = decltype(small_tag)::value;
         for (int s = lane; s < total; s += 32) {
-            const int jr = s / side;
+            const int jr = SMALL ? (int)__umulhi((unsigned)s, magic) : s / side;
             const int i_off = i_lo + (s - jr * side);
             const int j_off = j_lo + jr;
-            const float* c = img + (size_t)(y + j_off) * pitch + (x + i_off);
-            const float dx = ldg(c + 1) - ldg(c - 1);
-            const float dy = ldg(c - pitch) - ldg(c + pitch);  // up minus down, sift.cpp:483
-            const float g2 = dx * dx + dy * dy;
+            const int ic = (y + j_off) * pitch + (x + i_off);   // 32-bit indices: a plane has < 2^31 elements
+            const int iu = ic - pitch, id = ic + pitch;
+            const float dx = ldg(img + ic + 1) - ldg(img + ic - 1);
+            const float dy = ldg(img + iu) - ldg(img + id);  // up minus down, sift.cpp:483
+            const float g2 = fmaf(dx, dx, __fmul_rn(dy, dy));
             const float mag = g2 >= kFltMin ? g2 * rsqrt_ftz(g2) : 0.f;
             const float ang = fast_atan2(dy, dx);
             const float wgt = exp_ftz((float)(i_off * i_off + j_off * j_off) * neg_inv_denom);
             int b = (int)roundf((ang + 3.14159265358979323846f) * bins_per_rad);
             b = (b < nb) ? b : 0;  // sift.cpp:489-490: bin 0 <-> angle -pi
             b = max(b, 0);
-            atomicAdd(&my_hist[b], __float2uint_rn(wgt * mag * fix));
+            atomicAdd(&my_hist[b], __float2uint_rn(__fmul_rn(__fmul_rn(wgt, mag), fix)));
         }
+        };
+        if (side <= 1024) sample_loop(std::true_type{}); else sample_loop(std::false_type{});
         __syncwarp();
         // lane 0 smooths (the reference's in-place, sequential 1/4-1/2-1/4 filter, sift.cpp:496-504:
         // bin i sees the already-updated bin i-1, and the last bin the already-updated bin 0); with
