@@ -471,6 +471,10 @@ constexpr int kMaxOriBins = 128;   // largest num_bins of the generic instantiat
 // NB > 0: compile-time bin count (36, the reference default); NB == 0: sp.num_bins at run time
 // (<= kMaxOriBins).  The sequential smoothing runs through shared memory in both.
 // CTAs per SM (the grid is exactly one wave): 4 0.099 ms at 4K, 5 0.091 ms, 6 0.090 ms
+#ifndef SB_ORI_UNROLL
+#define SB_ORI_UNROLL 1
+#endif
+constexpr int ORI_UNROLL = SB_ORI_UNROLL;   // sample-loop unrolling of k_orient: 2 measured 0.0865 ms against 0.0849 at 1
 #ifndef SB_ORI_CTAS
 #define SB_ORI_CTAS 5
 #endif
@@ -523,6 +527,7 @@ k_orient(const PyramidDesc* __restrict__ pyr, const KpCore* __restrict__ raw, Kp
         const unsigned magic = side > 0 ? (unsigned)((0x100000000ull + (unsigned)side - 1u) / (unsigned)side) : 0u;
         auto sample_loop = [&](auto small_tag) {
         constexpr bool SMALL = decltype(small_tag)::value;
+#pragma unroll ORI_UNROLL
         for (int s = lane; s < total; s += 32) {
             const int jr = SMALL ? (int)__umulhi((unsigned)s, magic) : s / side;
             const int i_off = i_lo + (s - jr * side);
