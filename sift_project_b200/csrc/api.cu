@@ -48,6 +48,9 @@ struct sift_b200_ctx {
     Counters* h_counters = nullptr;  // pinned
     float* d_range = nullptr;        // (min, max) of a float input
     Cand* d_cands = nullptr;
+    CandCube* d_cubes = nullptr;   // the fit's first neighbourhood of candidate slot < cube_cap, written by the scan
+    int cube_cap = 0;
+    bool use_cubes = true;         // SIFT_B200_CUBES=0: the refinement loads every neighbourhood itself
     KpCore* d_raw = nullptr;
     KpCore* d_oriented = nullptr;
     uint8_t* d_records = nullptr;  // cap_final x 168
@@ -293,6 +296,7 @@ int enqueue_body(sift_b200_ctx* c, const DetectPlan& pl, bool forked, int* n_lau
     // the tail: the run of last octaves that are at most one 32 x 32 tile per SM each -- one launch for their
     // cascades, one for their extrema scans (default plan only: the kernel-form switches keep one launch per octave,
     // which is also what the tests compare the tail against)
+    const int cube_cap = (c->use_cubes && extrema_hands_cubes(sp.border, c->extrema_form)) ? c->cube_cap : 0;
     int tail_first = pl.octaves;
     if (pl.fused && c->use_tail && c->fused_mode == 0) {
         while (tail_first > 0 && tail_eligible(c->pyr.oct[tail_first - 1], c->sm_count)) --tail_first;
@@ -305,13 +309,13 @@ int enqueue_body(sift_b200_ctx* c, const DetectPlan& pl, bool forked, int* n_lau
             CU(c, launch_tail(c->pyr.oct, o, pl.octaves, pl.taps, c->keep_planes, (int*)(c->d_counters + 1), c->sm_count, s));
             mark(SIFT_B200_STAGE_PYRAMID, 1);
             if (extrema_multi_supported(sp.border, c->extrema_form)) {
-                CU(c, launch_extrema_multi(c->pyr.oct, o, n, pl.dogs, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, s));
+                CU(c, launch_extrema_multi(c->pyr.oct, o, n, pl.dogs, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, c->d_cubes, cube_cap, s));
                 mark(SIFT_B200_STAGE_EXTREMA, 1);
             } else {
                 for (int q = o; q < pl.octaves; ++q) {
                     const OctaveDesc& oq = c->pyr.oct[q];
                     if (oq.w < 2 * sp.border + 1 || oq.h < 2 * sp.border + 1) continue;
-                    CU(c, launch_extrema(oq, q, pl.dogs, sp.border, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, c->extrema_form, s));
+                    CU(c, launch_extrema(oq, q, pl.dogs, sp.border, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, c->d_cubes, cube_cap, c->extrema_form, s));
                     mark(SIFT_B200_STAGE_EXTREMA, 1);
                 }
             }
@@ -354,7 +358,7 @@ int enqueue_body(sift_b200_ctx* c, const DetectPlan& pl, bool forked, int* n_lau
                 CU(c, cudaStreamWaitEvent(s3, c->fork_ev[kMaxOctaves + 1 + o], 0));
                 s3_forked = true;
             }
-            CU(c, launch_extrema(od, o, pl.dogs, sp.border, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, c->extrema_form, s3));
+            CU(c, launch_extrema(od, o, pl.dogs, sp.border, sp.dog_threshold, c->d_cands, c->cap_extrema, c->d_counters, c->d_cubes, cube_cap, c->extrema_form, s3));
             mark(SIFT_B200_STAGE_EXTREMA, 1);
         }
     }
@@ -366,7 +370,7 @@ int enqueue_body(sift_b200_ctx* c, const DetectPlan& pl, bool forked, int* n_lau
         CU(c, cudaEventRecord(c->fork_ev[2 * kMaxOctaves + 1], c->side2));
         CU(c, cudaStreamWaitEvent(s, c->fork_ev[2 * kMaxOctaves + 1], 0));
     }
-    CU(c, launch_refine(c->d_pyr, c->d_cands, c->d_raw, c->d_counters, sp, c->sm_count, s));
+    CU(c, launch_refine(c->d_pyr, c->d_cands, c->d_raw, c->d_counters, c->d_cubes, cube_cap, sp, c->sm_count, s));
     mark(SIFT_B200_STAGE_REFINE, 1);
     CU(c, launch_orient(c->d_pyr, c->d_raw, c->d_oriented, c->d_counters, sp, c->sm_count, s));
     mark(SIFT_B200_STAGE_ORIENT, 1);
@@ -503,8 +507,8 @@ int enqueue_detect(sift_b200_ctx* c, const T* d_pixels, int width, int height, i
     std::vector<uint8_t> key;
     auto put = [&](const void* q, size_t n) { key.insert(key.end(), (const uint8_t*)q, (const uint8_t*)q + n); };
     put(&pl, sizeof pl); put(&sp, sizeof sp); put(&c->pyr, sizeof c->pyr); put(&c->ss.nb, sizeof(int));
-    const int dbg[7] = {c->keep_planes, c->force_unfused, c->fused_mode, c->extrema_form, c->three_branches,
-                        (int)std::min<long long>(c->fork_min_px, 1ll << 30), c->use_tail};
+    const int dbg[8] = {c->keep_planes, c->force_unfused, c->fused_mode, c->extrema_form, c->three_branches,
+                        (int)std::min<long long>(c->fork_min_px, 1ll << 30), c->use_tail, c->use_cubes};
     put(dbg, sizeof dbg);
     if (!c->graph_exec || key != c->graph_key) {
         if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
@@ -647,6 +651,8 @@ int sift_b200_create(int device, int max_width, int max_height, sift_b200_ctx** 
     if (const char* m = getenv("SIFT_B200_EXTREMA")) c->extrema_form = atoi(m);
     if (const char* m = getenv("SIFT_B200_FORK_MIN_PX")) c->fork_min_px = atoll(m);
     if (const char* m = getenv("SIFT_B200_TAIL")) c->use_tail = atoi(m) != 0;
+    int cube_cap_env = 0;   // SIFT_B200_CUBES: 0 = off, 1 = on, n > 1 = hand over the first n candidates only (tests)
+    if (const char* m = getenv("SIFT_B200_CUBES")) { c->use_cubes = atoi(m) != 0; cube_cap_env = atoi(m) > 1 ? atoi(m) : 0; }
     c->max_w = max_width;
     c->max_h = max_height;
 #define CRT(call)                                                                                   \
@@ -682,6 +688,9 @@ int sift_b200_create(int device, int max_width, int max_height, sift_b200_ctx** 
     c->cap_raw = (int)std::max<size_t>(1 << 15, px / 8);
     c->cap_oriented = (int)std::max<size_t>(1 << 15, px / 8);
     CRT(cudaMalloc(&c->d_cands, (size_t)c->cap_extrema * sizeof(Cand)));
+    c->cube_cap = std::min(c->cap_extrema, 1 << 20);   // 80 B each; candidates beyond it are fetched by the refinement
+    if (cube_cap_env) c->cube_cap = std::min(c->cube_cap, cube_cap_env);
+    CRT(cudaMalloc(&c->d_cubes, (size_t)c->cube_cap * sizeof(CandCube)));
     CRT(cudaMalloc(&c->d_raw, (size_t)c->cap_raw * sizeof(KpCore)));
     CRT(cudaMalloc(&c->d_oriented, (size_t)c->cap_oriented * sizeof(KpCore)));
     CRT(cudaMalloc(&c->d_records, (size_t)c->cap_oriented * 168));
@@ -709,7 +718,7 @@ void sift_b200_destroy(sift_b200_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->side) cudaStreamSynchronize(c->side);
     collection_free(c);
-    void* ptrs[] = {c->arena, c->d_input, c->d_pyr, c->d_counters, c->d_range, c->d_cands, c->d_raw, c->d_oriented,
+    void* ptrs[] = {c->arena, c->d_input, c->d_pyr, c->d_counters, c->d_range, c->d_cands, c->d_cubes, c->d_raw, c->d_oriented,
                     c->d_records, c->d_desc, c->ss.bucket_cnt, c->ss.bucket_off, c->ss.bucket_fill,
                     c->ss.uniq_cnt, c->ss.uniq_off, c->ss.perm, c->ss.tmp_sorted, c->ss.sorted,
                     c->ss.final_order, c->ms.part_idx, c->ms.part_d1, c->ms.part_d2, c->ms.norms_a,

@@ -37,6 +37,13 @@ struct Cand {
     int x, y, z, o;
 };
 
+// The 19 cells of a candidate's 3x3x3 DoG neighbourhood that the quadratic fit reads (sift.cpp:49-80: centre, 6 face
+// and 12 edge neighbours, no corners), handed over by the extrema scan -- which has just read them -- so that the first
+// fit of a candidate needs no scattered loads.  Order: see emit_cube in detect.cu.
+struct CandCube {
+    float v[20];
+};
+
 // The non-descriptor part of the reference's Keypoint (sift.hh:15-21), 40 bytes.
 struct KpCore {
     double x, y;

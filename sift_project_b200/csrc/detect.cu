@@ -201,6 +201,37 @@ k_extrema(const OctaveDesc oct, int octave, float thr, Cand* __restrict__ cands,
 // ~37 instructions per pixel against ~105 of the one-column form.  Same candidate set (the list is unordered).
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// CandCube slot of cube cell [dz][dx][dy] (get_pixel_cube's indexing, sift.cpp:32-44); corners are not stored (-1)
+__host__ __device__ constexpr int cube_slot(int dz, int dx, int dy) {
+    const int off = (dz != 1) + (dx != 1) + (dy != 1);
+    if (off == 0) return 0;
+    if (off == 1) return dz != 1 ? (dz == 0 ? 1 : 2) : dx != 1 ? (dx == 0 ? 3 : 4) : (dy == 0 ? 5 : 6);
+    if (off == 2) {
+        if (dy == 1) return 7 + (dz == 2 ? 0 : 2) + (dx == 2 ? 0 : 1);    // 7 c221, 8 c201, 9 c021, 10 c001
+        if (dx == 1) return 11 + (dz == 2 ? 0 : 2) + (dy == 2 ? 0 : 1);   // 11 c212, 12 c210, 13 c012, 14 c010
+        return 15 + (dy == 0 ? 0 : 2) + (dx == 0 ? 0 : 1);                // 15 c100, 16 c120, 17 c102, 18 c122
+    }
+    return -1;
+}
+// The scan hands the fit its first cube: the 19 cells are in this warp's L1 lines (it loaded rows y-1..y+1 of all
+// planes within the last three iterations), where the refinement kernel would fetch them from DRAM one sector at a time.
+__device__ __forceinline__ void emit_cube(const OctaveDesc& oc, int x, int y, int z, CandCube* __restrict__ out) {
+    float v[20];
+    v[19] = 0.f;
+#pragma unroll
+    for (int dz = 0; dz < 3; ++dz) {
+        const float* plane = oc.D[z + dz - 1] + (unsigned)y * (unsigned)oc.pitch + (unsigned)x;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+                if (cube_slot(dz, dx, dy) >= 0) v[cube_slot(dz, dx, dy)] = __ldg(plane + (dy - 1) * oc.pitch + (dx - 1));
+    }
+    float4* o4 = reinterpret_cast<float4*>(out->v);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
 constexpr int EX4_STRIP = 124;   // tested columns per warp: 128 loaded minus 2 on each side (kept a multiple of 4)
 // SLOTS = rows of the rotating register window (3 in use + SLOTS - 3 in flight), CTAS = CTAs per SM
 // XW = 1: the 4 warps of a CTA take consecutive row bands of one strip; XW = 4: they take 4 adjacent strips of one
@@ -208,7 +239,7 @@ constexpr int EX4_STRIP = 124;   // tested columns per warp: 128 loaded minus 2 
 template <int ND, int SLOTS, int XW>
 __device__ __forceinline__ void extrema4_body(const OctaveDesc& oct, int octave, float thr, int rows,
                                               Cand* __restrict__ cands, int cap, Counters* __restrict__ counters,
-                                              int bx, int by) {
+                                              CandCube* __restrict__ cubes, int cube_cap, int bx, int by) {
     constexpr int NZ = ND - 2;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -277,12 +308,17 @@ __device__ __forceinline__ void extrema4_body(const OctaveDesc& oct, int octave,
                 if (lane >= d) incl += t;
             }
             int slot = 0;
+#ifdef SB_EXP_NOATOM   // timing experiment only (wrong results): what the slot round trip costs the scan
+            if (lane == 31) slot = (int)((((unsigned)y * 2654435761u) ^ ((unsigned)x0 * 40503u)) % (unsigned)(cap - 256));
+#else
             if (lane == 31) slot = atomicAdd(&counters->n_extrema, incl);
+#endif
             slot = __shfl_sync(FULL, slot, 31) + incl - cnt;
             while (hits) {
                 const int b = __ffs(hits) - 1;
                 hits &= hits - 1;
                 if (slot < cap) cands[slot] = Cand{x0 + (b & 3), y, 1 + (b >> 2), octave};
+                if (slot < cube_cap) emit_cube(oct, x0 + (b & 3), y, 1 + (b >> 2), cubes + slot);
                 ++slot;
             }
         }
@@ -304,8 +340,8 @@ __device__ __forceinline__ void extrema4_body(const OctaveDesc& oct, int octave,
 template <int ND, int SLOTS, int CTAS, int XW>
 __global__ void __launch_bounds__(128, CTAS)
 k_extrema4(const OctaveDesc oct, int octave, float thr, int rows, Cand* __restrict__ cands, int cap,
-           Counters* __restrict__ counters) {
-    extrema4_body<ND, SLOTS, XW>(oct, octave, thr, rows, cands, cap, counters, blockIdx.x, blockIdx.y);
+           Counters* __restrict__ counters, CandCube* __restrict__ cubes, int cube_cap) {
+    extrema4_body<ND, SLOTS, XW>(oct, octave, thr, rows, cands, cap, counters, cubes, cube_cap, blockIdx.x, blockIdx.y);
 }
 
 // The scans of the small octaves (the ones k_tail produced) in one launch: a CTA finds its octave in a prefix table
@@ -319,16 +355,15 @@ struct ExtremaMulti {
 };
 template <int ND>
 __global__ void __launch_bounds__(128, 3)
-k_extrema4_multi(const ExtremaMulti m, float thr, Cand* __restrict__ cands, int cap, Counters* __restrict__ counters) {
+k_extrema4_multi(const ExtremaMulti m, float thr, Cand* __restrict__ cands, int cap, Counters* __restrict__ counters,
+                 CandCube* __restrict__ cubes, int cube_cap) {
     int i = 0;
     while ((int)blockIdx.x >= m.cta_begin[i + 1]) ++i;
     const int k = blockIdx.x - m.cta_begin[i];
     const int gx = m.gx[i];
-    OctaveDesc od;
-    od.w = m.oct[i].w; od.h = m.oct[i].h; od.pitch = m.oct[i].pitch;
-#pragma unroll
-    for (int z = 0; z < ND; ++z) od.D[z] = m.oct[i].D[z];
-    extrema4_body<ND, 4, 4>(od, m.octave[i], thr, m.rows[i], cands, cap, counters, k % gx, k / gx);
+    // (the octave is read where it lies in parameter space: a local copy would have to live in local memory, because
+    // the cube hand-over indexes its plane pointers with the run-time layer)
+    extrema4_body<ND, 4, 4>(m.oct[i], m.octave[i], thr, m.rows[i], cands, cap, counters, cubes, cube_cap, k % gx, k / gx);
 }
 
 // Generic window (window_size = 5, 7: border = 2, 3): the same tie-tolerant test over the
@@ -369,7 +404,9 @@ struct Fit {
     double off[3], g[3], hxx, hyy, hxy, centre;
 };
 
-__device__ Fit fit_cell(const OctaveDesc& oc, int x, int y, int z) {
+// load(dz, dx, dy) = DoG value of cube cell [dz][dx][dy]: from the planes, or from the cube the scan handed over
+template <typename Load>
+__device__ __forceinline__ Fit fit_cell(Load load) {
     double c[3][3][3];
 #pragma unroll
     for (int dz = 0; dz < 3; ++dz)
@@ -377,8 +414,7 @@ __device__ Fit fit_cell(const OctaveDesc& oc, int x, int y, int z) {
         for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
-                c[dz][dx][dy] =
-                    (double)ldg(oc.D[z + dz - 1] + (size_t)(y + dy - 1) * oc.pitch + (x + dx - 1)) / 255.0;
+                c[dz][dx][dy] = cube_slot(dz, dx, dy) >= 0 ? (double)load(dz, dx, dy) / 255.0 : 0.0;
     Fit f;
     f.centre = c[1][1][1];
     f.g[0] = 0.5 * (c[2][1][1] - c[0][1][1]);
@@ -405,9 +441,12 @@ __device__ Fit fit_cell(const OctaveDesc& oc, int x, int y, int z) {
     return f;
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef SB_REFINE_CTAS
+#define SB_REFINE_CTAS 10   // 48 registers: every candidate of a 4K image resident at once; measured (ms at 4K, with the cube hand-over) 6: 0.066, 8: 0.064, 10: 0.056
+#endif
+__global__ void __launch_bounds__(128, SB_REFINE_CTAS)
 k_refine(const PyramidDesc* __restrict__ pyr, const Cand* __restrict__ cands, KpCore* __restrict__ raw,
-         Counters* __restrict__ counters, const StageParams sp) {
+         Counters* __restrict__ counters, const CandCube* __restrict__ cubes, int cube_cap, const StageParams sp) {
     const int n = min(counters->n_extrema, sp.cap_extrema);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Cand e = cands[i];
@@ -416,7 +455,20 @@ k_refine(const PyramidDesc* __restrict__ pyr, const Cand* __restrict__ cands, Kp
         Fit f;
         bool keep = false;
         for (int step = 0; step < 5; ++step) {  // MAX_CONVERGENCE_STEPS, sift.hh:7
-            f = fit_cell(oc, x, y, layer);
+            if (step == 0 && i < cube_cap) {   // the first cube came with the candidate
+                float v[20];
+                const float4* c4 = reinterpret_cast<const float4*>(cubes[i].v);
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const float4 t = __ldg(c4 + q);
+                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                }
+                f = fit_cell([&](int dz, int dx, int dy) { return v[cube_slot(dz, dx, dy) >= 0 ? cube_slot(dz, dx, dy) : 0]; });
+            } else {
+                f = fit_cell([&](int dz, int dx, int dy) {
+                    return ldg(oc.D[layer + dz - 1] + (size_t)(y + dy - 1) * oc.pitch + (x + dx - 1));
+                });
+            }
             const double m = fmax(fabs(f.off[0]), fmax(fabs(f.off[1]), fabs(f.off[2])));
             if (m < 0.5) {  // CONVERGENCE_THR, sift.hh:8
                 const double dot = f.g[0] * f.off[0] + f.g[1] * f.off[1] + f.g[2] * f.off[2];
@@ -1094,7 +1146,7 @@ cudaError_t launch_range(const float* px, size_t n, float* range, int sm_count, 
 static int extrema4_rows(long long px);
 
 cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int border, int threshold, Cand* cands,
-                           int cap, Counters* counters, int form, cudaStream_t s) {
+                           int cap, Counters* counters, CandCube* cubes, int cube_cap, int form, cudaStream_t s) {
     if (oct.w < 2 * border + 1 || oct.h < 2 * border + 1) return cudaSuccess;
     if (border != 1) {
         dim3 grid((oct.w - 2 * border + 255) / 256, oct.h - 2 * border);
@@ -1108,8 +1160,8 @@ cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int bord
         dim3 grid(oct.w / EX4_STRIP + 1, (oct.h - 2 + 4 * rows - 1) / (4 * rows));
         const int strips = oct.w / EX4_STRIP + 1;
         const dim3 grid_x((strips + 3) / 4, (oct.h - 2 + rows - 1) / rows);   // XW = 4: warps side by side
-#define SB_EX4(ND, SL, CT) k_extrema4<ND, SL, CT, 1><<<grid, 128, 0, s>>>(oct, octave, (float)threshold, rows, cands, cap, counters)
-#define SB_EX4X(ND, SL, CT) k_extrema4<ND, SL, CT, 4><<<grid_x, 128, 0, s>>>(oct, octave, (float)threshold, rows, cands, cap, counters)
+#define SB_EX4(ND, SL, CT) k_extrema4<ND, SL, CT, 1><<<grid, 128, 0, s>>>(oct, octave, (float)threshold, rows, cands, cap, counters, cubes, cube_cap)
+#define SB_EX4X(ND, SL, CT) k_extrema4<ND, SL, CT, 4><<<grid_x, 128, 0, s>>>(oct, octave, (float)threshold, rows, cands, cap, counters, cubes, cube_cap)
         // measured at 4K (all octaves, ms): warps side by side 0.279, warps stacked 0.290; a deeper window (5 / 6
         // slots) 0.307 / 0.349, 4 CTAs per SM 0.290 / 0.279 (no gain), no prefetch slot 0.316
         switch (dogs) {
@@ -1154,7 +1206,7 @@ bool extrema_multi_supported(int border, int form) { return border == 1 && form 
 
 // octaves first .. first + n - 1 in one launch (window 3 only); same candidate set as n launch_extrema calls
 cudaError_t launch_extrema_multi(const OctaveDesc* octs, int first, int n, int dogs, int threshold, Cand* cands, int cap,
-                                 Counters* counters, cudaStream_t s) {
+                                 Counters* counters, CandCube* cubes, int cube_cap, cudaStream_t s) {
     if (n > kMaxExtremaMulti) return cudaErrorInvalidValue;
     ExtremaMulti m;
     memset(&m, 0, sizeof m);
@@ -1175,18 +1227,20 @@ cudaError_t launch_extrema_multi(const OctaveDesc* octs, int first, int n, int d
     m.cta_begin[m.n] = total;
     if (total == 0) return cudaSuccess;
     switch (dogs) {
-        case 4: k_extrema4_multi<4><<<total, 128, 0, s>>>(m, (float)threshold, cands, cap, counters); break;
-        case 5: k_extrema4_multi<5><<<total, 128, 0, s>>>(m, (float)threshold, cands, cap, counters); break;
-        case 6: k_extrema4_multi<6><<<total, 128, 0, s>>>(m, (float)threshold, cands, cap, counters); break;
-        case 7: k_extrema4_multi<7><<<total, 128, 0, s>>>(m, (float)threshold, cands, cap, counters); break;
+        case 4: k_extrema4_multi<4><<<total, 128, 0, s>>>(m, (float)threshold, cands, cap, counters, cubes, cube_cap); break;
+        case 5: k_extrema4_multi<5><<<total, 128, 0, s>>>(m, (float)threshold, cands, cap, counters, cubes, cube_cap); break;
+        case 6: k_extrema4_multi<6><<<total, 128, 0, s>>>(m, (float)threshold, cands, cap, counters, cubes, cube_cap); break;
+        case 7: k_extrema4_multi<7><<<total, 128, 0, s>>>(m, (float)threshold, cands, cap, counters, cubes, cube_cap); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
+bool extrema_hands_cubes(int border, int form) { return border == 1 && form != 1; }
+
 cudaError_t launch_refine(const PyramidDesc* d_pyr, const Cand* cands, KpCore* raw, Counters* counters,
-                          const StageParams& sp, int sm_count, cudaStream_t s) {
-    k_refine<<<sm_count * 16, 128, 0, s>>>(d_pyr, cands, raw, counters, sp);
+                          const CandCube* cubes, int cube_cap, const StageParams& sp, int sm_count, cudaStream_t s) {
+    k_refine<<<sm_count * 16, 128, 0, s>>>(d_pyr, cands, raw, counters, cubes, cube_cap, sp);
     return cudaGetLastError();
 }
 

@@ -47,13 +47,16 @@ cudaError_t launch_canary_plane(const float* plane, int w, int h, int pitch, uns
                                 unsigned long long* counts, int sm_count, cudaStream_t s);
 cudaError_t launch_canary_tail(const void* p, size_t words, unsigned pattern, unsigned long long* counts, int sm_count,
                                cudaStream_t s);
+// cubes / cube_cap: the scan also writes the fit's first 3x3x3 neighbourhood of candidate slot < cube_cap (only the
+// kernels for which extrema_hands_cubes() is true; pass the same cube_cap to launch_refine, 0 otherwise)
+bool extrema_hands_cubes(int border, int form);
 cudaError_t launch_extrema(const OctaveDesc& oct, int octave, int dogs, int border, int threshold, Cand* cands,
-                           int cap, Counters* counters, int form, cudaStream_t s);
+                           int cap, Counters* counters, CandCube* cubes, int cube_cap, int form, cudaStream_t s);
 bool extrema_multi_supported(int border, int form);
 cudaError_t launch_extrema_multi(const OctaveDesc* octs, int first, int n, int dogs, int threshold, Cand* cands, int cap,
-                                 Counters* counters, cudaStream_t s);
-cudaError_t launch_refine(const PyramidDesc* d_pyr, const Cand* cands, KpCore* raw,
-                          Counters* counters, const StageParams& sp, int sm_count, cudaStream_t s);
+                                 Counters* counters, CandCube* cubes, int cube_cap, cudaStream_t s);
+cudaError_t launch_refine(const PyramidDesc* d_pyr, const Cand* cands, KpCore* raw, Counters* counters,
+                          const CandCube* cubes, int cube_cap, const StageParams& sp, int sm_count, cudaStream_t s);
 cudaError_t launch_orient(const PyramidDesc* d_pyr, const KpCore* raw, KpCore* oriented,
                           Counters* counters, const StageParams& sp, int sm_count, cudaStream_t s);
 cudaError_t launch_sort_dedup(const KpCore* oriented, Counters* counters, const SortScratch& ss,

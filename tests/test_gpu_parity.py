@@ -227,6 +227,19 @@ def test_tail_kernel_equals_octave_by_octave_launches(ctx):
     ctx.debug_options()
 
 
+def test_cube_handover_equals_refinement_loads(synth, monkeypatch):
+    """The extrema scan hands the quadratic fit its first 3x3x3 neighbourhood (CandCube); the refinement must get
+    the same numbers as when it loads them itself: all off, all on, and only the first 500 candidates handed
+    over (the rest take the load path) give the same bytes."""
+    imgs = [synth["image"], O.synth_image(301, 517, seed=3), O.synth_image(97, 131, seed=5)]
+    out = {}
+    for mode in ("0", "1", "500"):
+        monkeypatch.setenv("SIFT_B200_CUBES", mode)
+        with S.SiftContext(1040, 768) as c:
+            out[mode] = [c.detect(im).tobytes() for im in imgs] + [c.detect(imgs[0], double_image_size=False).tobytes()]
+    assert out["0"] == out["1"] == out["500"]
+
+
 def test_graph_replay_equals_plain_launches(ctx, synth):
     """The CUDA-graph launch plan (forked octave chain) and plain single-stream launches run the same kernels on
     the same data: identical bytes; one graph per image size / parameter set, re-captured only on a change."""
