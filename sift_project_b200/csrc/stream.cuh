@@ -206,7 +206,7 @@ __device__ __forceinline__ void stream_level(const CascadeArgs& a, const CUtenso
 
     float* gout = a.g[L - 1];
     float* dout = a.d[L - 1];
-    float* decp = LAST ? a.dec : nullptr;
+    float* decp = (LAST && G::NL == 3) ? a.dec : nullptr;   // only the three-level kernel (G0 -> G3) feeds the next octave
 
     // acc[p] = partial sum of output row (i - R + 1 + p) after input row i: 2R rows are in flight
     float2 acc[2 * R][C2];
