@@ -586,8 +586,9 @@ k_input_u8(const uint8_t* __restrict__ src, int sw, int sh, float* __restrict__ 
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
     const bool inside = tx0 - IN_R >= 0 && ty0 - IN_R >= 0 && tx0 + TW + IN_R <= w && ty0 + TH + IN_R <= h;
     auto px = [&](int x, int y) -> V {   // gray level of source pixel (x, y)
-        if (CH == 1) return (V)__ldg(src + (size_t)y * sw + x);
-        const uint8_t* p = src + ((size_t)y * sw + x) * 3;
+        // (32-bit indices: the context's image has < 2^31 bytes even as RGB; checked at creation)
+        if (CH == 1) return (V)__ldg(src + (y * sw + x));
+        const uint8_t* p = src + (y * sw + x) * 3;
         return (V)gray_bt709((double)__ldg(p), (double)__ldg(p + 1), (double)__ldg(p + 2));
     };
     const V c = (V)centre, half = (V)0.5;
